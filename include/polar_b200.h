@@ -1,0 +1,151 @@
+/*
+ * polar_b200.h -- C ABI of libpolar_b200.so: the B200 (sm_100a) batched polar decoders.
+ *
+ * This is the drop-in boundary for the decode() hot path of the reference's `PolarDecoder` pybind11
+ * module.  The reference has no C ABI of its own: its boundary is the pybind11 classes
+ * registered in PolarDecoder/PolarDecoder/_cpp/_libPolarDecoder.cpp:29-50.  Each entry point below states
+ * which reference interface it replaces ("PD/" = PolarDecoder/PolarDecoder/_cpp/).  The pybind11 module
+ * shipped in this repo (quantized_decoder_polar_codes_b200/csrc/pb_pybind.cpp) re-creates those 15 classes
+ * on top of this header; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Plain pointers and sizes only; no torch / pybind types.  All functions return a pd_status; the text of
+ * the last error on the calling thread is available from pd_last_error().
+ */
+#ifndef POLAR_B200_H
+#define POLAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One value per reference class; replaces the 15 py::class_ registrations (PD/py_interface/py_*.cpp). */
+typedef enum pd_kind {
+    PD_SC = 0,             /* SCDecoder                  PD/src/SCDecoder.cpp:14-89 */
+    PD_FASTSC = 1,         /* FastSCDecoder              PD/src/FastSCDecoder.cpp:21-173 */
+    PD_SCL = 2,            /* SCLDecoder                 PD/src/SCLDecoder.cpp:38-175 */
+    PD_FASTSCL = 3,        /* FastSCLDecoder             PD/src/FastSCLDecoder.cpp:49-423 */
+    PD_CASCL = 4,          /* CASCLDecoder               PD/src/CASCLDecoder.cpp:74-249 */
+    PD_SCLUT = 5,          /* SCLUTDecoder               PD/src/SCLUTDecoder.cpp:21-124 */
+    PD_FASTSCLUT = 6,      /* FastSCLUTDecoder           PD/src/FastSCLUT.cpp:27-206 */
+    PD_SCLLUT = 7,         /* SCLLUTDecoder              PD/src/SCLLUTDecoder.cpp:47-253 */
+    PD_FASTSCLLUT = 8,     /* FastSCLLUTDecoder          PD/src/FastSCLLUTDecoder.cpp:57-408 */
+    PD_CASCLLUT = 9,       /* CASCLLUTDecoder            PD/src/CASCLLUTDecoder.cpp:65-303 */
+    PD_CAFASTSCLLUT = 10,  /* CAFastSCLLUTDecoder        PD/src/CAFastSCLLUTDecoder.cpp:60-454 */
+    PD_SC_UNIFORM = 11,    /* SCUniformQuantizedDecoder  PD/src/SCUniformQuantizedDecoder.cpp:20-99 */
+    PD_SCL_UNIFORM = 12,   /* SCLUniformQuantizedDecoder PD/src/SCLUniformQuantizedDecoder.cpp:43-184 */
+    PD_SC_LLOYD = 13,      /* SCLloydQuantizedDecoder    PD/src/SCLloydQuantizedDecoder.cpp:22-101 */
+    PD_SCL_LLOYD = 14,     /* SCLLloydQuantizedDecoder   PD/src/SCLLloydQuantizedDecoder.cpp:46-187 */
+    PD_KIND_COUNT = 15
+} pd_kind;
+
+typedef enum pd_dtype {
+    PD_U8 = 0,   /* channel symbols, one byte each (LUT family; the compact streaming format)       */
+    PD_I32 = 1,  /* channel symbols as the reference's py::array_t<int> (LUT family)                */
+    PD_F64 = 2   /* channel LLRs as the reference's py::array_t<double> (float/uniform/Lloyd family) */
+} pd_dtype;
+
+typedef enum pd_status {
+    PD_OK = 0,
+    PD_EINVAL = 1,   /* bad argument / inconsistent tables (the reference: undefined behaviour)  */
+    PD_ECUDA = 2,    /* CUDA runtime error or no usable sm_100 device                           */
+    PD_ERANGE = 3,   /* an input symbol is outside the root table (the reference: out-of-bounds read) */
+    PD_ENOMEM = 4
+} pd_status;
+
+/*
+ * Constructor arguments, i.e. what the reference's py::init<...> signatures carry
+ * (PD/py_interface/py_*.cpp), with the nested Python lists flattened:
+ *
+ *   LUT_f[node][pos][a][b]      -> lut_pool[f_off[node] + (pos*f_qa[node] + a)*f_qb[node] + b]
+ *   LUT_g[node][pos][u][a][b]   -> lut_pool[g_off[node] + ((pos*2+u)*g_qa[node] + a)*g_qb[node] + b]
+ *        node = heap id (1<<depth)+index-1 in [0,N-1); f_npos/g_npos[node] = number of per-position tables
+ *        stored for the node: 1 (one table shared by all positions -- what every generator of the reference
+ *        emits) or N>>(depth+1).
+ *   virtual_channel_llr[level][pos][sym] -> llr_pool[llr_off[level*N+pos] + sym]; llr_off has
+ *        llr_levels*N+1 entries so row lengths are known.
+ * Unused members are NULL / 0.  All arrays are copied; the caller may free them after pd_create returns.
+ */
+typedef struct pd_config {
+    int32_t kind;                 /* pd_kind */
+    int32_t N, K, A, L;           /* A: CA kinds only; L: list kinds only */
+    int32_t device;               /* CUDA device ordinal */
+    const int32_t *frozen_bits;   /* [N], 1 = frozen (indicator mask, mainFPDecoder.py:49,58) */
+    const int32_t *node_type;     /* [2N-1] Fast kinds: -1 ordinary, 0 R0, 1 R1, 2 REP, 3 SPC (IdentifyNodes.py) */
+    int32_t crc_n;                /* CASCL only: generator degree and its set exponent positions    */
+    const int32_t *crc_loc;       /*   (crc_p of PD/py_interface/py_CASCLDecoder.cpp:9-11)           */
+    int32_t crc_loc_len;
+    const int32_t *lut_pool;
+    int64_t lut_pool_len;
+    const int64_t *f_off, *g_off;                 /* [N-1] */
+    const int32_t *f_npos, *g_npos;               /* [N-1] */
+    const int32_t *f_qa, *f_qb, *g_qa, *g_qb;     /* [N-1] */
+    const double *llr_pool;
+    const int64_t *llr_off;                       /* [llr_levels*N + 1] */
+    int32_t llr_levels;
+    const double *decoder_r_f, *decoder_r_g;      /* [N-1] uniform kinds */
+    int32_t v;                                    /* uniform + Lloyd kinds */
+    const double *boundaries_f, *boundaries_g;    /* [N-1][n_boundaries] Lloyd kinds */
+    const double *reconstruction_f, *reconstruction_g; /* [N-1][n_reconstruction] */
+    int32_t n_boundaries, n_reconstruction;
+} pd_config;
+
+typedef struct pd_decoder pd_decoder; /* opaque; owns device copies of all tables + the compiled schedule */
+
+/* Replaces `T(N, K, ...)` of each reference class: validates, packs the tables, compiles the tree walk
+ * into a device schedule, uploads everything to `cfg->device`. */
+int pd_create(const pd_config *cfg, pd_decoder **out);
+void pd_destroy(pd_decoder *dec);
+
+/* Number of bytes written per frame: K, or A for the CRC-aided kinds (PD/src/SCLLUTDecoder.cpp:245,
+ * CASCLLUTDecoder.cpp:290). */
+int pd_out_len(const pd_decoder *dec);
+int pd_code_len(const pd_decoder *dec);
+
+/* Replaces `T::decode(array)` (e.g. SCLLUT::decode, PD/src/SCLLUTDecoder.cpp:47) for a batch of B frames.
+ * host_in: [B][N] of `in_dtype`, C-contiguous; host_out: [B][pd_out_len] uint8.  Blocking: pipelines
+ * host->device copies, the decode kernel and device->host copies in chunks, then synchronizes.
+ * Decoding is stateless across calls like the reference's; a decoder object must not be used from two
+ * threads at once. */
+int pd_decode(pd_decoder *dec, const void *host_in, int in_dtype, int64_t B, uint8_t *host_out);
+
+/* Same with device-resident buffers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).
+ * Input symbol range errors are reported by the next pd_check(). */
+int pd_decode_device(pd_decoder *dec, const void *dev_in, int in_dtype, int64_t B, uint8_t *dev_out,
+                     void *cuda_stream);
+/* Synchronizes `cuda_stream` and returns PD_ERANGE if any frame decoded since the last check carried an
+ * out-of-range symbol, PD_ECUDA on a CUDA error. */
+int pd_check(pd_decoder *dec, void *cuda_stream);
+
+/* Optional debug taps (tests of the float family compare path metrics with the oracle): after this call
+ * every pd_decode_device also writes the final path metrics [B][L] (slot order) and the winning slot [B].
+ * Pass NULLs to switch off. */
+int pd_set_debug_outputs(pd_decoder *dec, double *dev_pm, int32_t *dev_winner);
+
+/* Simulation-mode counters (the BER/BLER bookkeeping of the drivers' frame loop,
+ * mainQuantizedDecoder_LLRDomain.py:181-192): adds #bit errors and #block errors of dev_decoded vs
+ * dev_truth ([B][len] each) to dev_counters[0], dev_counters[1] (device uint64).  These two words are what
+ * the multi-GPU front-end all-reduces over NCCL. */
+int pd_count_errors(const uint8_t *dev_decoded, const uint8_t *dev_truth, int64_t B, int32_t len,
+                    unsigned long long *dev_counters, void *cuda_stream);
+
+/* Kernels launched by this library on the calling process so far (bench.py reports it as gpu_launches). */
+int64_t pd_launch_count(void);
+/* Name of the kernel variant pd_decode* uses for this decoder ("generic", "scl_lut_warp", ...). */
+const char *pd_kernel_name(const pd_decoder *dec);
+/* Static description of the schedule for reports: n_steps, algorithmic lookups per frame, ... */
+int pd_schedule_stats(const pd_decoder *dec, int64_t *n_steps, int64_t *elem_ops, int64_t *n_sorts);
+
+/* Pinned host memory for the caller's I/O buffers (pd_decode is PCIe-bound from pageable memory). */
+void *pd_host_alloc(size_t bytes);
+void pd_host_free(void *p);
+
+const char *pd_last_error(void);
+const char *pd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLAR_B200_H */

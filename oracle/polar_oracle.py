@@ -83,7 +83,7 @@ def flatten_lut(N, lut, is_g):
     cur = 0
     for p in range(N - 1):
         t = np.asarray(lut[p], dtype=np.int32)
-        want = 5 if is_g else 4
+        want = 4 if is_g else 3
         if t.ndim == want - 1:          # a single table for the node (compact form)
             t = t[None]
         assert t.ndim == want, f"node {p}: bad LUT rank {t.ndim}"

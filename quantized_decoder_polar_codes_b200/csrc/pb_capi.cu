@@ -1,0 +1,573 @@
+// libpolar_b200.so -- C ABI (include/polar_b200.h) over the sm_100a decoder kernels.
+// Host side: validates the constructor arguments the reference classes take, packs the lookup tables to
+// bytes, replays the reference's data-independent tree walk once into a linear schedule, uploads
+// everything, and launches the kernels.  No CPU decode path exists here: without a CUDA device every
+// entry point fails with PD_ECUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/polar_b200.h"
+#include "pb_generic.cuh"
+#include "pb_internal.h"
+#include "pb_scl_lut.cuh"
+
+using namespace pb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) return fail(PD_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));    \
+    } while (0)
+
+bool is_lut(int k) { return k >= PD_SCLUT && k <= PD_CAFASTSCLLUT; }
+bool is_list(int k) {
+    return k == PD_SCL || k == PD_FASTSCL || k == PD_CASCL || k == PD_SCLLUT || k == PD_FASTSCLLUT ||
+           k == PD_CASCLLUT || k == PD_CAFASTSCLLUT || k == PD_SCL_UNIFORM || k == PD_SCL_LLOYD;
+}
+bool is_fast(int k) {
+    return k == PD_FASTSC || k == PD_FASTSCL || k == PD_FASTSCLUT || k == PD_FASTSCLLUT || k == PD_CAFASTSCLLUT;
+}
+bool is_ca(int k) { return k == PD_CASCL || k == PD_CASCLLUT || k == PD_CAFASTSCLLUT; }
+int domain_of(int k) {
+    if (is_lut(k)) return DOM_LUT;
+    if (k == PD_SC_UNIFORM || k == PD_SCL_UNIFORM) return DOM_UNIFORM;
+    if (k == PD_SC_LLOYD || k == PD_SCL_LLOYD) return DOM_LLOYD;
+    return DOM_FLOAT;
+}
+
+struct StreamSlot {
+    cudaStream_t stream = nullptr;
+    void *d_in = nullptr;
+    uint8_t *d_out = nullptr;
+    char *ws = nullptr;
+    size_t in_cap = 0, out_cap = 0, ws_cap = 0;
+};
+
+}  // namespace
+
+struct pd_decoder {
+    Dev dev{};
+    int device = 0;
+    int sm_count = 0;
+    std::vector<void *> allocs;
+    std::vector<Step> steps;
+    int64_t elem_ops = 0, n_sorts = 0;
+    // generic kernel launch geometry
+    int threads = 32;
+    size_t ws_bytes = 0;      // per-CTA workspace
+    int use_smem = 0;
+    int ctas_per_sm = 1;
+    // specialised kernel
+    FastPlan fast{};
+    const char *kernel_name = "generic";
+    int *d_err = nullptr;
+    double *dbg_pm = nullptr;
+    int32_t *dbg_win = nullptr;
+    char *ws_user = nullptr;  // workspace for pd_decode_device (global-memory variant)
+    size_t ws_user_cap = 0;
+    StreamSlot slot[2];
+    int64_t chunk_frames = 0;
+};
+
+namespace {
+
+template <typename T>
+int upload(pd_decoder *D, const std::vector<T> &h, const T **out) {
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    D->allocs.push_back(p);
+    if (!h.empty()) CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T *>(p);
+    return PD_OK;
+}
+
+bool special_type(int kind, int t) {
+    if (!is_fast(kind)) return false;
+    if (t < 0) return false;
+    return is_list(kind) ? t <= 2 : t <= 3;   // list variants expand SPC nodes
+}
+
+struct Builder {
+    const pd_config *cfg;
+    int N, n, kind;
+    std::vector<Step> steps;
+    int64_t elem_ops = 0, n_sorts = 0;
+    int r1_tmax = 0;
+    void walk(int d, uint32_t node) {
+        if (d == n) {
+            steps.push_back(Step{OP_LEAF, (uint8_t)d, (uint8_t)(cfg->frozen_bits[node] == 1), 0, node});
+            if (is_list(kind) && cfg->frozen_bits[node] != 1) n_sorts++;
+            return;
+        }
+        int p = (1 << d) + (int)node - 1;
+        if (is_fast(kind)) {
+            int t = cfg->node_type[p];
+            if (special_type(kind, t)) {
+                static const uint8_t ops[4] = {OP_R0, OP_R1, OP_REP, OP_SPC};
+                steps.push_back(Step{ops[t], (uint8_t)d, 0, 0, node});
+                int temp = N >> d;
+                if (is_list(kind)) {
+                    if (t == 1) { r1_tmax = std::max(r1_tmax, temp); n_sorts += std::min(cfg->L - 1, temp); }
+                    if (t == 2) n_sorts++;
+                }
+                return;
+            }
+        }
+        steps.push_back(Step{OP_F, (uint8_t)d, 0, 0, node});
+        elem_ops += N >> (d + 1);
+        walk(d + 1, 2 * node);
+        steps.push_back(Step{OP_G, (uint8_t)d, 0, 0, node});
+        elem_ops += N >> (d + 1);
+        walk(d + 1, 2 * node + 1);
+        steps.push_back(Step{OP_C, (uint8_t)d, 0, 0, node});
+    }
+};
+
+int build_lut(pd_decoder *D, const pd_config *c) {
+    const int N = c->N, n = D->dev.n, kind = c->kind;
+    if (!c->lut_pool || !c->f_off || !c->g_off || !c->f_npos || !c->g_npos || !c->f_qa || !c->f_qb || !c->g_qa ||
+        !c->g_qb || !c->llr_pool || !c->llr_off)
+        return fail(PD_EINVAL, "LUT decoder needs LUT_f, LUT_g and virtual_channel_llr");
+    if (c->llr_levels < n) return fail(PD_EINVAL, "virtual_channel_llr has %d levels, need >= %d", c->llr_levels, n);
+    auto llr_len = [&](int level, int pos) -> int64_t {
+        int64_t r = (int64_t)level * N + pos;
+        return c->llr_off[r + 1] - c->llr_off[r];
+    };
+    // bound that the values of child (cd,cn), element j, must respect
+    auto consumer_bound = [&](int cd, uint32_t cn, int j) -> int64_t {
+        int ct = N >> cd;
+        if (cd == n) return llr_len(n - 1, (int)cn);
+        int cp = (1 << cd) + (int)cn - 1;
+        if (is_fast(kind) && special_type(kind, c->node_type[cp])) return llr_len(cd - 1, (int)(cn * (uint32_t)ct) + j);
+        int half = ct / 2;
+        return j < half ? std::min(c->f_qa[cp], c->g_qa[cp]) : std::min(c->f_qb[cp], c->g_qb[cp]);
+    };
+    std::vector<NodeTab> tabs(N - 1);
+    std::vector<uint8_t> pool;
+    pool.reserve(1 << 20);
+    for (int d = 0; d < n; ++d) {
+        for (uint32_t node = 0; node < (1u << d); ++node) {
+            int p = (1 << d) + (int)node - 1;
+            int ct = N >> (d + 1);
+            NodeTab &tb = tabs[p];
+            for (int isg = 0; isg < 2; ++isg) {
+                int qa = isg ? c->g_qa[p] : c->f_qa[p], qb = isg ? c->g_qb[p] : c->f_qb[p];
+                int npos = isg ? c->g_npos[p] : c->f_npos[p];
+                int64_t off = isg ? c->g_off[p] : c->f_off[p];
+                int planes = isg ? 2 : 1;
+                if (qa < 1 || qb < 1 || qa > 256 || qb > 256) return fail(PD_EINVAL, "node %d: table dims %dx%d unsupported (1..256)", p, qa, qb);
+                if (npos != 1 && npos < ct) return fail(PD_EINVAL, "node %d: %d per-position tables, need 1 or >= %d", p, npos, ct);
+                int64_t per = (int64_t)planes * qa * qb;
+                if (off < 0 || off + per * (npos == 1 ? 1 : ct) > c->lut_pool_len) return fail(PD_EINVAL, "node %d: table outside lut_pool", p);
+                int stored = (npos == 1) ? 1 : ct;
+                // per-position tables that are all equal collapse to one (every generator of the reference emits that)
+                if (stored > 1) {
+                    bool same = true;
+                    for (int j = 1; j < stored && same; ++j)
+                        same = memcmp(c->lut_pool + off, c->lut_pool + off + per * j, (size_t)per * sizeof(int32_t)) == 0;
+                    if (same) stored = 1;
+                }
+                uint32_t base = (uint32_t)pool.size();
+                uint32_t cn = 2 * node + (uint32_t)isg;
+                for (int j = 0; j < stored; ++j) {
+                    int64_t bound = std::numeric_limits<int64_t>::max();
+                    if (stored == 1) for (int jj = 0; jj < ct; ++jj) bound = std::min(bound, consumer_bound(d + 1, cn, jj));
+                    else bound = consumer_bound(d + 1, cn, j);
+                    const int32_t *src = c->lut_pool + off + per * j;
+                    for (int64_t e = 0; e < per; ++e) {
+                        int32_t v = src[e];
+                        if (v < 0 || v >= bound || v > 255)
+                            return fail(PD_EINVAL, "LUT_%s[%d]: entry %d is outside the consumer alphabet [0,%lld)", isg ? "g" : "f", p, v, (long long)std::min<int64_t>(bound, 256));
+                        pool.push_back((uint8_t)v);
+                    }
+                }
+                if (isg) { tb.g_off = base; tb.g_sz = (uint32_t)(qa * qb); tb.g_qb = (uint16_t)qb; tb.g_pstride = stored == 1 ? 0 : (uint32_t)per; }
+                else { tb.f_off = base; tb.f_sz = (uint32_t)(qa * qb); tb.f_qb = (uint16_t)qb; tb.f_pstride = stored == 1 ? 0 : (uint32_t)per; }
+            }
+        }
+    }
+    D->dev.root_qa = std::min(c->f_qa[0], c->g_qa[0]);
+    D->dev.root_qb = std::min(c->f_qb[0], c->g_qb[0]);
+    int64_t rows = (int64_t)c->llr_levels * N;
+    int64_t total = c->llr_off[rows];
+    if (total > (int64_t)0x7fffffff) return fail(PD_EINVAL, "virtual_channel_llr too large");
+    std::vector<uint32_t> loff(rows);
+    for (int64_t r = 0; r < rows; ++r) {
+        if (c->llr_off[r + 1] < c->llr_off[r]) return fail(PD_EINVAL, "llr_off not monotone");
+        loff[r] = (uint32_t)c->llr_off[r];
+    }
+    std::vector<double> llr(c->llr_pool, c->llr_pool + total);
+    int rc;
+    if ((rc = upload(D, pool, &D->dev.lut))) return rc;
+    if ((rc = upload(D, tabs, &D->dev.tabs))) return rc;
+    if ((rc = upload(D, llr, &D->dev.llr))) return rc;
+    if ((rc = upload(D, loff, &D->dev.llr_off))) return rc;
+    plan_fast_lut(D->dev, D->steps, tabs, pool, c->frozen_bits, &D->fast);
+    return PD_OK;
+}
+
+template <int DOM, bool LIST>
+int launch_generic_t(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws, int grid) {
+    size_t smem = D->use_smem ? D->ws_bytes : 0;
+    if (D->threads == 32)
+        generic_decode_kernel<DOM, LIST, true><<<grid, 32, smem, s>>>(D->dev, d_in, dtype, d_out, B, ws, D->ws_bytes, D->use_smem, D->d_err, D->dbg_pm, D->dbg_win);
+    else
+        generic_decode_kernel<DOM, LIST, false><<<grid, D->threads, smem, s>>>(D->dev, d_in, dtype, d_out, B, ws, D->ws_bytes, D->use_smem, D->d_err, D->dbg_pm, D->dbg_win);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PD_OK;
+}
+
+template <int DOM, bool LIST>
+const void *generic_fn(bool warp) {
+    return warp ? (const void *)generic_decode_kernel<DOM, LIST, true> : (const void *)generic_decode_kernel<DOM, LIST, false>;
+}
+const void *generic_fn_for(const pd_decoder *D) {
+    bool w = D->threads == 32;
+    bool l = D->dev.list != 0;
+    switch (D->dev.domain) {
+    case DOM_LUT: return l ? generic_fn<DOM_LUT, true>(w) : generic_fn<DOM_LUT, false>(w);
+    case DOM_FLOAT: return l ? generic_fn<DOM_FLOAT, true>(w) : generic_fn<DOM_FLOAT, false>(w);
+    case DOM_UNIFORM: return l ? generic_fn<DOM_UNIFORM, true>(w) : generic_fn<DOM_UNIFORM, false>(w);
+    default: return l ? generic_fn<DOM_LLOYD, true>(w) : generic_fn<DOM_LLOYD, false>(w);
+    }
+}
+
+int generic_grid(const pd_decoder *D, int64_t B) {
+    int64_t g = (int64_t)D->sm_count * D->ctas_per_sm;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, B));
+}
+
+int launch_generic(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws) {
+    int grid = generic_grid(D, B);
+    bool l = D->dev.list != 0;
+    switch (D->dev.domain) {
+    case DOM_LUT: return l ? launch_generic_t<DOM_LUT, true>(D, d_in, dtype, B, d_out, s, ws, grid) : launch_generic_t<DOM_LUT, false>(D, d_in, dtype, B, d_out, s, ws, grid);
+    case DOM_FLOAT: return l ? launch_generic_t<DOM_FLOAT, true>(D, d_in, dtype, B, d_out, s, ws, grid) : launch_generic_t<DOM_FLOAT, false>(D, d_in, dtype, B, d_out, s, ws, grid);
+    case DOM_UNIFORM: return l ? launch_generic_t<DOM_UNIFORM, true>(D, d_in, dtype, B, d_out, s, ws, grid) : launch_generic_t<DOM_UNIFORM, false>(D, d_in, dtype, B, d_out, s, ws, grid);
+    default: return l ? launch_generic_t<DOM_LLOYD, true>(D, d_in, dtype, B, d_out, s, ws, grid) : launch_generic_t<DOM_LLOYD, false>(D, d_in, dtype, B, d_out, s, ws, grid);
+    }
+}
+
+int plan_generic(pd_decoder *D) {
+    const Dev &d = D->dev;
+    int L = d.list ? d.L : 1;
+    size_t vsz = d.domain == DOM_LUT ? 1 : 8;
+    size_t ws = (size_t)L * d.N * vsz + (size_t)L * d.r1_tmax * (8 + 4) + (size_t)L * 3 * d.N + (size_t)2 * L * d.r1_tmax + d.N;
+    ws = (ws + 15) & ~(size_t)15;
+    D->ws_bytes = ws;
+    int64_t work = (int64_t)L * d.N / 2;
+    int th = 32;
+    while (th < 256 && th * 8 < work) th *= 2;
+    D->threads = th;
+    D->use_smem = ws <= 96 * 1024;
+    const void *fn = generic_fn_for(D);
+    if (D->use_smem) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, th, D->use_smem ? ws : 0));
+    if (occ < 1) return fail(PD_ECUDA, "generic kernel does not fit on the device (ws=%zu)", ws);
+    D->ctas_per_sm = occ;
+    return PD_OK;
+}
+
+bool want_fast(const pd_decoder *D, int dtype) { return D->fast.ok && dtype != PD_F64; }
+
+int launch(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws) {
+    if (B <= 0) return PD_OK;
+    if (want_fast(D, dtype)) {
+        int rc = launch_fast_lut(D->dev, D->fast, d_in, dtype, B, d_out, s, D->d_err, D->dbg_pm, D->dbg_win, D->sm_count);
+        g_launches++;
+        if (rc != 0) return fail(PD_ECUDA, "fast kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        return PD_OK;
+    }
+    return launch_generic(D, d_in, dtype, B, d_out, s, ws);
+}
+
+size_t dtype_size(int t) { return t == PD_U8 ? 1 : t == PD_I32 ? 4 : 8; }
+
+int check_dtype(const pd_decoder *D, int t) {
+    if (D->dev.domain == DOM_LUT) {
+        if (t != PD_U8 && t != PD_I32) return fail(PD_EINVAL, "LUT decoders take PD_U8 or PD_I32 symbols");
+    } else if (t != PD_F64) {
+        return fail(PD_EINVAL, "float/uniform/Lloyd decoders take PD_F64 LLRs");
+    }
+    return PD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pd_last_error(void) { return g_err.c_str(); }
+const char *pd_version(void) { return "polar_b200 0.1 (sm_100a)"; }
+int64_t pd_launch_count(void) { return g_launches.load(); }
+
+void pd_destroy(pd_decoder *D) {
+    if (!D) return;
+    cudaSetDevice(D->device);
+    for (auto &sl : D->slot) {
+        if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        cudaFree(sl.d_in); cudaFree(sl.d_out); cudaFree(sl.ws);
+    }
+    cudaFree(D->ws_user);
+    for (void *p : D->allocs) cudaFree(p);
+    free_fast_plan(&D->fast);
+    delete D;
+}
+
+int pd_create(const pd_config *c, pd_decoder **out) {
+    if (!c || !out) return fail(PD_EINVAL, "null argument");
+    *out = nullptr;
+    const int kind = c->kind, N = c->N;
+    if (kind < 0 || kind >= PD_KIND_COUNT) return fail(PD_EINVAL, "unknown decoder kind %d", kind);
+    if (N < 2 || N > (1 << kMaxLog) || (N & (N - 1))) return fail(PD_EINVAL, "N=%d must be a power of two in [2,%d]", N, 1 << kMaxLog);
+    if (!c->frozen_bits) return fail(PD_EINVAL, "frozen_bits missing");
+    int n = 0;
+    while ((1 << n) < N) n++;
+    const bool list = is_list(kind), fastk = is_fast(kind), ca = is_ca(kind);
+    if (list && (c->L < 1 || c->L > kMaxL)) return fail(PD_EINVAL, "L=%d must be in [1,%d]", c->L, kMaxL);
+    std::vector<int32_t> info_pos;
+    for (int i = 0; i < N; ++i) if (c->frozen_bits[i] == 0) info_pos.push_back(i);
+    if ((int)info_pos.size() != c->K) return fail(PD_EINVAL, "K=%d but frozen_bits has %zu non-frozen positions", c->K, info_pos.size());
+    if (c->K < 1) return fail(PD_EINVAL, "K must be >= 1");
+    if (fastk) {
+        if (!c->node_type) return fail(PD_EINVAL, "node_type missing");
+        if (special_type(kind, c->node_type[0])) return fail(PD_EINVAL, "degenerate code: the root itself is a special node (the reference reads level -1 here)");
+    }
+    int crc_n = 0, crc_check = 0;
+    uint32_t taps = 0;
+    if (ca) {
+        if (c->A < 1 || c->A > c->K) return fail(PD_EINVAL, "A=%d must be in [1,K]", c->A);
+        std::vector<int> poly;
+        if (kind == PD_CASCL) {   // honours the ctor polynomial, compares crc_n bits (PD/src/CASCLDecoder.cpp:49-53,222)
+            crc_n = c->crc_n;
+            if (crc_n < 1 || crc_n > 32) return fail(PD_EINVAL, "crc_n=%d unsupported (1..32)", crc_n);
+            poly.assign(crc_n + 1, 0);
+            for (int i = 0; i < c->crc_loc_len; ++i) {
+                if (c->crc_loc[i] < 0 || c->crc_loc[i] > crc_n) return fail(PD_EINVAL, "crc_p entry out of range");
+                poly[c->crc_loc[i]] = 1;
+            }
+            crc_check = crc_n;
+        } else {                  // hard-coded CRC-24, compares K-A bits (PD/include/CASCLLUTDecoder.h:33-34, CASCLLUTDecoder.cpp:280)
+            static const int loc[13] = {24, 23, 21, 20, 17, 15, 13, 12, 8, 4, 2, 1, 0};
+            crc_n = 24;
+            poly.assign(25, 0);
+            for (int l : loc) poly[l] = 1;
+            crc_check = c->K - c->A;
+            if (crc_check > 24) return fail(PD_EINVAL, "K-A=%d > 24: the reference reads past its 24 check bits", crc_check);
+        }
+        if (c->A + crc_check > c->K) return fail(PD_EINVAL, "A + checked CRC bits exceeds K");
+        for (int k = 0; k < crc_n; ++k) if (poly[1 + k]) taps |= 1u << (crc_n - 1 - k);
+    }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PD_ECUDA, "no CUDA device: libpolar_b200 has no CPU path");
+    if (c->device < 0 || c->device >= ndev) return fail(PD_EINVAL, "device %d out of range", c->device);
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10) return fail(PD_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", c->device, prop.major, prop.minor);
+
+    pd_decoder *D = new pd_decoder();
+    D->device = c->device;
+    D->sm_count = prop.multiProcessorCount;
+    Dev &d = D->dev;
+    d.kind = kind; d.N = N; d.n = n; d.K = c->K; d.A = c->A; d.L = list ? c->L : 1;
+    d.Kout = ca ? c->A : c->K;
+    d.domain = domain_of(kind); d.list = list; d.fast = fastk; d.ca = ca;
+    d.pm_init = (kind == PD_SCL || kind == PD_CASCL || kind == PD_SCL_UNIFORM || kind == PD_SCL_LLOYD) ? 1e300 : std::numeric_limits<double>::infinity();
+    d.crc_n = crc_n; d.crc_check = crc_check; d.crc_taps = taps;
+
+    Builder b{c, N, n, kind};
+    b.walk(0, 0);
+    D->steps = b.steps;
+    D->elem_ops = b.elem_ops; D->n_sorts = b.n_sorts;
+    d.r1_tmax = b.r1_tmax;
+    d.n_steps = (int)b.steps.size();
+    int rc = PD_OK;
+    auto bail = [&](int code) { pd_destroy(D); return code; };
+    if ((rc = upload(D, b.steps, &d.steps))) return bail(rc);
+    if ((rc = upload(D, info_pos, &d.info_pos))) return bail(rc);
+
+    if (d.domain == DOM_LUT) {
+        if ((rc = build_lut(D, c))) return bail(rc);
+    } else if (d.domain == DOM_UNIFORM) {
+        if (!c->decoder_r_f || !c->decoder_r_g) return bail(fail(PD_EINVAL, "decoder_r_f / decoder_r_g missing"));
+        std::vector<double> rf(c->decoder_r_f, c->decoder_r_f + N - 1), rg(c->decoder_r_g, c->decoder_r_g + N - 1);
+        if ((rc = upload(D, rf, &d.r_f)) || (rc = upload(D, rg, &d.r_g))) return bail(rc);
+        d.mf_mul = double(c->v / 2 - 0.5);
+        d.mg_mul = double(c->v / 2 - 1);
+    } else if (d.domain == DOM_LLOYD) {
+        if (!c->boundaries_f || !c->boundaries_g || !c->reconstruction_f || !c->reconstruction_g) return bail(fail(PD_EINVAL, "Lloyd tables missing"));
+        if (c->n_boundaries < 1 || c->n_reconstruction < 1) return bail(fail(PD_EINVAL, "Lloyd table widths missing"));
+        size_t nbs = (size_t)(N - 1) * c->n_boundaries, nrs = (size_t)(N - 1) * c->n_reconstruction;
+        std::vector<double> bf(c->boundaries_f, c->boundaries_f + nbs), bg(c->boundaries_g, c->boundaries_g + nbs);
+        std::vector<double> rf(c->reconstruction_f, c->reconstruction_f + nrs), rg(c->reconstruction_g, c->reconstruction_g + nrs);
+        if ((rc = upload(D, bf, &d.bnd_f)) || (rc = upload(D, bg, &d.bnd_g)) || (rc = upload(D, rf, &d.rec_f)) || (rc = upload(D, rg, &d.rec_g))) return bail(rc);
+        d.nb = c->n_boundaries; d.nr = c->n_reconstruction;
+    }
+    {
+        void *p = nullptr;
+        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return bail(fail(PD_ECUDA, "cudaMalloc failed"));
+        D->allocs.push_back(p);
+        D->d_err = (int *)p;
+        cudaMemset(p, 0, sizeof(int));
+    }
+    if ((rc = plan_generic(D))) return bail(rc);
+    D->kernel_name = D->fast.ok ? D->fast.name : "generic";
+    // frames per pipeline chunk of pd_decode: ~32 MB of input per chunk
+    size_t in_frame = (size_t)N * (d.domain == DOM_LUT ? 4 : 8);
+    D->chunk_frames = std::max<int64_t>(1024, (int64_t)((32u << 20) / in_frame));
+    *out = D;
+    return PD_OK;
+}
+
+int pd_out_len(const pd_decoder *D) { return D ? D->dev.Kout : 0; }
+int pd_code_len(const pd_decoder *D) { return D ? D->dev.N : 0; }
+const char *pd_kernel_name(const pd_decoder *D) { return D ? D->kernel_name : ""; }
+
+int pd_schedule_stats(const pd_decoder *D, int64_t *n_steps, int64_t *elem_ops, int64_t *n_sorts) {
+    if (!D) return fail(PD_EINVAL, "null decoder");
+    if (n_steps) *n_steps = (int64_t)D->steps.size();
+    if (elem_ops) *elem_ops = D->elem_ops;
+    if (n_sorts) *n_sorts = D->n_sorts;
+    return PD_OK;
+}
+
+int pd_set_debug_outputs(pd_decoder *D, double *dev_pm, int32_t *dev_winner) {
+    if (!D) return fail(PD_EINVAL, "null decoder");
+    D->dbg_pm = dev_pm;
+    D->dbg_win = dev_winner;
+    return PD_OK;
+}
+
+int pd_decode_device(pd_decoder *D, const void *dev_in, int in_dtype, int64_t B, uint8_t *dev_out, void *cuda_stream) {
+    if (!D || (B > 0 && (!dev_in || !dev_out))) return fail(PD_EINVAL, "null argument");
+    int rc = check_dtype(D, in_dtype);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(D->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    char *ws = nullptr;
+    if (!want_fast(D, in_dtype) && !D->use_smem) {
+        size_t need = D->ws_bytes * (size_t)generic_grid(D, B);
+        if (need > D->ws_user_cap) {
+            CUDA_TRY(cudaDeviceSynchronize());
+            cudaFree(D->ws_user);
+            D->ws_user = nullptr; D->ws_user_cap = 0;
+            CUDA_TRY(cudaMalloc((void **)&D->ws_user, need));
+            D->ws_user_cap = need;
+        }
+        ws = D->ws_user;
+    }
+    return launch(D, dev_in, in_dtype, B, dev_out, s, ws);
+}
+
+int pd_check(pd_decoder *D, void *cuda_stream) {
+    if (!D) return fail(PD_EINVAL, "null decoder");
+    CUDA_TRY(cudaSetDevice(D->device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    int h = 0;
+    CUDA_TRY(cudaMemcpy(&h, D->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h) {
+        cudaMemset(D->d_err, 0, sizeof(int));
+        return fail(PD_ERANGE, "an input symbol is outside the root lookup table (valid: [0,%d) for the first half, [0,%d) for the second)", D->dev.root_qa, D->dev.root_qb);
+    }
+    return PD_OK;
+}
+
+int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8_t *host_out) {
+    if (!D || (B > 0 && (!host_in || !host_out))) return fail(PD_EINVAL, "null argument");
+    int rc = check_dtype(D, in_dtype);
+    if (rc) return rc;
+    if (B <= 0) return PD_OK;
+    CUDA_TRY(cudaSetDevice(D->device));
+    const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
+    const int64_t chunk = std::min<int64_t>(B, D->chunk_frames);
+    const bool need_ws = !want_fast(D, in_dtype) && !D->use_smem;
+    for (auto &sl : D->slot) {
+        if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        size_t in_need = (size_t)chunk * N * esz, out_need = (size_t)chunk * Ko;
+        if (sl.in_cap < in_need) { cudaFree(sl.d_in); sl.d_in = nullptr; sl.in_cap = 0; CUDA_TRY(cudaMalloc(&sl.d_in, in_need)); sl.in_cap = in_need; }
+        if (sl.out_cap < out_need) { cudaFree(sl.d_out); sl.d_out = nullptr; sl.out_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.d_out, out_need)); sl.out_cap = out_need; }
+        if (need_ws) {
+            size_t ws_need = D->ws_bytes * (size_t)generic_grid(D, chunk);
+            if (sl.ws_cap < ws_need) { cudaFree(sl.ws); sl.ws = nullptr; sl.ws_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.ws, ws_need)); sl.ws_cap = ws_need; }
+        }
+    }
+    int which = 0;
+    for (int64_t f0 = 0; f0 < B; f0 += chunk, which ^= 1) {
+        StreamSlot &sl = D->slot[which];
+        int64_t nb = std::min<int64_t>(chunk, B - f0);
+        CUDA_TRY(cudaMemcpyAsync(sl.d_in, (const char *)host_in + (size_t)f0 * N * esz, (size_t)nb * N * esz, cudaMemcpyHostToDevice, sl.stream));
+        if ((rc = launch(D, sl.d_in, in_dtype, nb, sl.d_out, sl.stream, sl.ws))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)f0 * Ko, sl.d_out, (size_t)nb * Ko, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(D->slot[0].stream));
+    return pd_check(D, D->slot[1].stream);
+}
+
+// ---- simulation-mode error counters -------------------------------------------------------------
+__global__ void count_errors_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, long long B, int len,
+                                    unsigned long long *counters) {
+    unsigned long long bits = 0, blocks = 0;
+    for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < B; f += (long long)gridDim.x * blockDim.x) {
+        const uint8_t *pa = a + (size_t)f * len, *pb = b + (size_t)f * len;
+        int e = 0;
+        for (int k = 0; k < len; ++k) e += (pa[k] != pb[k]);
+        bits += e;
+        blocks += (e != 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        bits += __shfl_down_sync(0xffffffffu, bits, o);
+        blocks += __shfl_down_sync(0xffffffffu, blocks, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bits) atomicAdd(&counters[0], bits);
+        if (blocks) atomicAdd(&counters[1], blocks);
+    }
+}
+
+int pd_count_errors(const uint8_t *dev_decoded, const uint8_t *dev_truth, int64_t B, int32_t len,
+                    unsigned long long *dev_counters, void *cuda_stream) {
+    if (B <= 0) return PD_OK;
+    if (!dev_decoded || !dev_truth || !dev_counters || len < 1) return fail(PD_EINVAL, "null argument");
+    int threads = 128;
+    int grid = (int)std::min<int64_t>((B + threads - 1) / threads, 148 * 8);
+    count_errors_kernel<<<grid, threads, 0, (cudaStream_t)cuda_stream>>>(dev_decoded, dev_truth, B, len, dev_counters);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PD_OK;
+}
+
+void *pd_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail(PD_ENOMEM, "cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void pd_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

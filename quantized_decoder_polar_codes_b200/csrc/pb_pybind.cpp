@@ -1,0 +1,317 @@
+// Host-side mirror of the reference's pybind11 module `_libPolarDecoder`
+// (PolarDecoder/PolarDecoder/_cpp/_libPolarDecoder.cpp:29-50 and py_interface/py_*.cpp): the same 15 class
+// names, constructor keyword names and `decode` argument names, implemented on top of the C ABI in
+// include/polar_b200.h.  Everything heavy happens behind that ABI on the GPU; this file only converts the
+// Python objects the reference drivers pass (nested lists / numpy arrays) into the flattened pd_config.
+//
+// Extensions over the reference surface (all optional, keyword-only in spirit):
+//   * decode() also accepts a (B,N) batch and then returns (B,K) -- the entry used for throughput;
+//   * every constructor takes device=<int> (default 0);
+//   * LUT_f / LUT_g entries may be given as one [Qa][Qb] / [2][Qa][Qb] table per node.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/polar_b200.h"
+
+namespace py = pybind11;
+
+namespace pb200 {
+
+using IArr = py::array_t<int32_t, py::array::c_style | py::array::forcecast>;
+using DArr = py::array_t<double, py::array::c_style | py::array::forcecast>;
+
+[[noreturn]] void raise_status(int rc) {
+    std::string msg = pd_last_error();
+    if (rc == PD_EINVAL || rc == PD_ERANGE) throw py::value_error(msg);
+    throw std::runtime_error(msg);
+}
+
+struct Tables {
+    std::vector<int32_t> frozen, node_type, crc_loc, lut_pool, f_npos, g_npos, f_qa, f_qb, g_qa, g_qb;
+    std::vector<int64_t> f_off, g_off, llr_off;
+    std::vector<double> llr_pool, r_f, r_g, bf, bg, rf, rg;
+    int llr_levels = 0, nb = 0, nr = 0;
+};
+
+std::vector<int32_t> to_ivec(const py::object &o) {
+    IArr a = IArr::ensure(o);
+    if (!a) throw py::value_error("expected an integer sequence");
+    return std::vector<int32_t>(a.data(), a.data() + a.size());
+}
+std::vector<double> to_dvec(const py::object &o) {
+    DArr a = DArr::ensure(o);
+    if (!a) throw py::value_error("expected a float sequence");
+    return std::vector<double>(a.data(), a.data() + a.size());
+}
+
+// LUT_f[node][pos][a][b] / LUT_g[node][pos][u][a][b]  (PD/src/SCLUTDecoder.cpp:57,88)
+void flatten_lut(const py::object &lut, int N, bool is_g, Tables &t) {
+    py::sequence seq = py::reinterpret_borrow<py::sequence>(lut);
+    if ((int)py::len(seq) < N - 1) throw py::value_error(std::string(is_g ? "LUT_g" : "LUT_f") + " needs N-1 node entries");
+    auto &off = is_g ? t.g_off : t.f_off;
+    auto &npos = is_g ? t.g_npos : t.f_npos;
+    auto &qa = is_g ? t.g_qa : t.f_qa;
+    auto &qb = is_g ? t.g_qb : t.f_qb;
+    const int want = is_g ? 4 : 3;
+    for (int p = 0; p < N - 1; ++p) {
+        IArr a = IArr::ensure(seq[p]);
+        if (!a) throw py::value_error("LUT node " + std::to_string(p) + ": not a regular integer array");
+        int nd = (int)a.ndim();
+        if (nd != want && nd != want - 1) throw py::value_error("LUT node " + std::to_string(p) + ": unexpected rank");
+        if (is_g && a.shape(nd - 3) != 2) throw py::value_error("LUT_g node " + std::to_string(p) + ": u axis must have 2 entries");
+        off.push_back((int64_t)t.lut_pool.size());
+        npos.push_back(nd == want ? (int32_t)a.shape(0) : 1);
+        qa.push_back((int32_t)a.shape(nd - 2));
+        qb.push_back((int32_t)a.shape(nd - 1));
+        t.lut_pool.insert(t.lut_pool.end(), a.data(), a.data() + a.size());
+    }
+}
+
+// virtual_channel_llr[level][pos][sym], possibly ragged in the last axis
+void flatten_llr(const py::object &llr, int N, Tables &t) {
+    py::sequence lv = py::reinterpret_borrow<py::sequence>(llr);
+    t.llr_levels = (int)py::len(lv);
+    t.llr_off.push_back(0);
+    for (int l = 0; l < t.llr_levels; ++l) {
+        py::object level = lv[l];
+        DArr whole;
+        try { whole = DArr::ensure(level); } catch (py::error_already_set &) { whole = DArr(); }
+        if (!whole) PyErr_Clear();
+        if (whole && whole.ndim() == 2 && whole.shape(0) >= N) {
+            int q = (int)whole.shape(1);
+            for (int pos = 0; pos < N; ++pos) {
+                t.llr_pool.insert(t.llr_pool.end(), whole.data() + (size_t)pos * q, whole.data() + (size_t)(pos + 1) * q);
+                t.llr_off.push_back((int64_t)t.llr_pool.size());
+            }
+            continue;
+        }
+        py::sequence rows = py::reinterpret_borrow<py::sequence>(level);
+        if ((int)py::len(rows) < N) throw py::value_error("virtual_channel_llr level needs N rows");
+        for (int pos = 0; pos < N; ++pos) {
+            std::vector<double> r = to_dvec(rows[pos]);
+            t.llr_pool.insert(t.llr_pool.end(), r.begin(), r.end());
+            t.llr_off.push_back((int64_t)t.llr_pool.size());
+        }
+    }
+}
+
+class Decoder {
+public:
+    Decoder() = default;
+    Decoder(const Decoder &) = delete;
+    Decoder &operator=(const Decoder &) = delete;
+    ~Decoder() { pd_destroy(dec_); }
+
+    void init(int kind, int N, int K, int A, int L, const py::object &frozen, const py::object &node_type, int crc_n,
+              const py::object &crc_p, const py::object &lut_f, const py::object &lut_g, const py::object &llr,
+              const py::object &r_f, const py::object &r_g, int v, const py::object &bf, const py::object &bg,
+              const py::object &rf, const py::object &rg, int device) {
+        Tables t;
+        pd_config c{};
+        c.kind = kind; c.N = N; c.K = K; c.A = A; c.L = L; c.device = device; c.v = v;
+        t.frozen = to_ivec(frozen);
+        if ((int)t.frozen.size() < N) throw py::value_error("frozen_bits must have N entries");
+        c.frozen_bits = t.frozen.data();
+        if (!node_type.is_none()) {
+            t.node_type = to_ivec(node_type);
+            if ((int)t.node_type.size() < N - 1) throw py::value_error("node_type must cover all internal nodes");
+            t.node_type.resize(2 * (size_t)N - 1, -1);
+            c.node_type = t.node_type.data();
+        }
+        if (!crc_p.is_none()) {
+            t.crc_loc = to_ivec(crc_p);
+            c.crc_n = crc_n; c.crc_loc = t.crc_loc.data(); c.crc_loc_len = (int)t.crc_loc.size();
+        }
+        if (!lut_f.is_none()) {
+            flatten_lut(lut_f, N, false, t);
+            flatten_lut(lut_g, N, true, t);
+            flatten_llr(llr, N, t);
+            c.lut_pool = t.lut_pool.data(); c.lut_pool_len = (int64_t)t.lut_pool.size();
+            c.f_off = t.f_off.data(); c.g_off = t.g_off.data();
+            c.f_npos = t.f_npos.data(); c.g_npos = t.g_npos.data();
+            c.f_qa = t.f_qa.data(); c.f_qb = t.f_qb.data(); c.g_qa = t.g_qa.data(); c.g_qb = t.g_qb.data();
+            c.llr_pool = t.llr_pool.data(); c.llr_off = t.llr_off.data(); c.llr_levels = t.llr_levels;
+        }
+        if (!r_f.is_none()) {
+            t.r_f = to_dvec(r_f); t.r_g = to_dvec(r_g);
+            if ((int)t.r_f.size() < N - 1 || (int)t.r_g.size() < N - 1) throw py::value_error("decoder_r_f / decoder_r_g need N-1 entries");
+            c.decoder_r_f = t.r_f.data(); c.decoder_r_g = t.r_g.data();
+        }
+        if (!bf.is_none()) {
+            auto grab = [&](const py::object &o, std::vector<double> &dst, int &width) {
+                DArr a = DArr::ensure(o);
+                if (!a || a.ndim() != 2 || a.shape(0) < N - 1) throw py::value_error("Lloyd tables must be [N-1][width] arrays");
+                width = (int)a.shape(1);
+                dst.assign(a.data(), a.data() + (size_t)(N - 1) * width);
+            };
+            int wb = 0, wb2 = 0, wr = 0, wr2 = 0;
+            grab(bf, t.bf, wb); grab(bg, t.bg, wb2); grab(rf, t.rf, wr); grab(rg, t.rg, wr2);
+            if (wb != wb2 || wr != wr2) throw py::value_error("f and g Lloyd tables must have equal widths");
+            c.boundaries_f = t.bf.data(); c.boundaries_g = t.bg.data();
+            c.reconstruction_f = t.rf.data(); c.reconstruction_g = t.rg.data();
+            c.n_boundaries = wb; c.n_reconstruction = wr;
+        }
+        int rc = pd_create(&c, &dec_);
+        if (rc != PD_OK) raise_status(rc);
+        N_ = N;
+        lut_ = !lut_f.is_none();
+    }
+
+    // decode((N,)) / ((1,N)) -> (K,) like the reference; decode((B,N)) -> (B,K)
+    py::array_t<uint8_t> decode(const py::object &x) {
+        const int ko = pd_out_len(dec_);
+        py::array arr;
+        int dtype;
+        if (lut_) {
+            py::array in = py::array::ensure(x);
+            if (!in) throw py::value_error("decode: expected an array");
+            if (py::isinstance<py::array_t<uint8_t>>(in) && (in.flags() & py::array::c_style)) {
+                arr = in; dtype = PD_U8;
+            } else {
+                arr = IArr::ensure(x);   // the reference takes py::array_t<int> with forcecast
+                dtype = PD_I32;
+            }
+        } else {
+            arr = DArr::ensure(x);
+            dtype = PD_F64;
+        }
+        if (!arr) throw py::value_error("decode: cannot convert the input");
+        int64_t B;
+        bool flat;
+        if (arr.ndim() == 1) {
+            if (arr.shape(0) < N_) throw py::value_error("decode: need at least N values");
+            B = 1; flat = true;   // the reference reads the first N elements only
+        } else if (arr.ndim() == 2 && arr.shape(1) == N_) {
+            B = arr.shape(0); flat = (B == 1);
+        } else {
+            throw py::value_error("decode: expected shape (N,), (1,N) or (B,N)");
+        }
+        py::array_t<uint8_t> out = flat ? py::array_t<uint8_t>(ko) : py::array_t<uint8_t>({(py::ssize_t)B, (py::ssize_t)ko});
+        int rc;
+        {
+            py::gil_scoped_release nogil;
+            rc = pd_decode(dec_, arr.data(), dtype, B, out.mutable_data());
+        }
+        if (rc != PD_OK) raise_status(rc);
+        return out;
+    }
+
+    std::string kernel() const { return pd_kernel_name(dec_); }
+    uintptr_t handle() const { return reinterpret_cast<uintptr_t>(dec_); }
+
+private:
+    pd_decoder *dec_ = nullptr;
+    int N_ = 0;
+    bool lut_ = false;
+};
+
+#define NONE py::none()
+
+// One distinct C++ type per reference class so that pybind11 registers 15 independent Python classes.
+template <int KIND> struct Cls : Decoder {};
+
+template <int KIND, typename... Extra>
+py::class_<Cls<KIND>> declare(py::module_ &m, const char *name, const char *doc, const char *decode_arg) {
+    py::class_<Cls<KIND>> c(m, name, doc);
+    c.def("decode", &Decoder::decode, py::arg(decode_arg));
+    c.def_property_readonly("kernel", &Decoder::kernel, "name of the CUDA kernel variant in use");
+    c.def_property_readonly("_handle", &Decoder::handle, "pd_decoder* for direct C-ABI calls");
+    return c;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+using py::arg;
+
+PYBIND11_MODULE(_libPolarDecoder, m) {
+    m.doc() = "Decoders For Polar Codes (B200 / sm_100a build behind the reference PolarDecoder API)";
+    m.attr("backend") = "polar_b200";
+    m.def("version", []() { return std::string(pd_version()); });
+    m.def("launch_count", []() { return pd_launch_count(); });
+
+#define MK(KIND) std::unique_ptr<Cls<KIND>> self(new Cls<KIND>())
+
+    // PD/py_interface/py_SCDecoder.cpp:9-11
+    declare<PD_SC>(m, "SCDecoder", "Successive Cancellation Decoder", "llr")
+        .def(py::init([](int N, int K, py::object fb, py::object mb, int device) {
+                 MK(PD_SC); self->init(PD_SC, N, K, 0, 1, fb, NONE, 0, NONE, NONE, NONE, NONE, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("frozen_bits"), arg("message_bits"), arg("device") = 0);
+    // py_FastSCDecoder.cpp:10-12
+    declare<PD_FASTSC>(m, "FastSCDecoder", "Fast Successive Cancellation Decoder", "llr")
+        .def(py::init([](int N, int K, py::object fb, py::object mb, py::object nt, int device) {
+                 MK(PD_FASTSC); self->init(PD_FASTSC, N, K, 0, 1, fb, nt, 0, NONE, NONE, NONE, NONE, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("frozen_bits"), arg("message_bits"), arg("node_type"), arg("device") = 0);
+    // py_SCLDecoder.cpp:10-12
+    declare<PD_SCL>(m, "SCLDecoder", "Successive Cancellation List Decoder", "llr")
+        .def(py::init([](int N, int K, int L, py::object fb, py::object mb, int device) {
+                 MK(PD_SCL); self->init(PD_SCL, N, K, 0, L, fb, NONE, 0, NONE, NONE, NONE, NONE, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("device") = 0);
+    // py_FastSCLDecoder.cpp:9-11
+    declare<PD_FASTSCL>(m, "FastSCLDecoder", "Fast Successive Cancellation List Decoder", "llr")
+        .def(py::init([](int N, int K, int L, py::object fb, py::object mb, py::object nt, int device) {
+                 MK(PD_FASTSCL); self->init(PD_FASTSCL, N, K, 0, L, fb, nt, 0, NONE, NONE, NONE, NONE, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("node_type"), arg("device") = 0);
+    // py_CASCLDecoder.cpp:9-11
+    declare<PD_CASCL>(m, "CASCLDecoder", "CRC Aided Successive Cancellation List Decoder", "llr")
+        .def(py::init([](int N, int K, int A, int L, py::object fb, py::object mb, int crc_n, py::object crc_p, int device) {
+                 MK(PD_CASCL); self->init(PD_CASCL, N, K, A, L, fb, NONE, crc_n, crc_p, NONE, NONE, NONE, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("A"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("crc_n"), arg("crc_p"), arg("device") = 0);
+    // py_SCLUTDecoder.cpp:10-14
+    declare<PD_SCLUT>(m, "SCLUTDecoder", "Successive Cancellation Decoder Using LUT", "channel_quantized_symbols")
+        .def(py::init([](int N, int K, py::object fb, py::object mb, py::object f, py::object g, py::object llr, int device) {
+                 MK(PD_SCLUT); self->init(PD_SCLUT, N, K, 0, 1, fb, NONE, 0, NONE, f, g, llr, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("frozen_bits"), arg("message_bits"), arg("LUT_f"), arg("LUT_g"), arg("virtual_channel_llr"), arg("device") = 0);
+    // py_FastSCLUTDecoder.cpp:11-15 (note LUT_Fs / LUT_Gs and decode(llr))
+    declare<PD_FASTSCLUT>(m, "FastSCLUTDecoder", "Fast Successive Cancellation Decoder Using LUT", "llr")
+        .def(py::init([](int N, int K, py::object fb, py::object mb, py::object nt, py::object f, py::object g, py::object llr, int device) {
+                 MK(PD_FASTSCLUT); self->init(PD_FASTSCLUT, N, K, 0, 1, fb, nt, 0, NONE, f, g, llr, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("frozen_bits"), arg("message_bits"), arg("node_type"), arg("LUT_Fs"), arg("LUT_Gs"), arg("virtual_channel_llr"), arg("device") = 0);
+    // py_SCLLUTDecoder.cpp:11-15
+    declare<PD_SCLLUT>(m, "SCLLUTDecoder", "Successive Cancellation List Decoder Using LUT", "channel_quantized_symbols")
+        .def(py::init([](int N, int K, int L, py::object fb, py::object mb, py::object f, py::object g, py::object llr, int device) {
+                 MK(PD_SCLLUT); self->init(PD_SCLLUT, N, K, 0, L, fb, NONE, 0, NONE, f, g, llr, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("LUT_f"), arg("LUT_g"), arg("virtual_channel_llr"), arg("device") = 0);
+    // py_FastSCLLUTDecoder.cpp:12-16
+    declare<PD_FASTSCLLUT>(m, "FastSCLLUTDecoder", "Fast Successive Cancellation List Decoder Using LUT", "channel_quantized_symbols")
+        .def(py::init([](int N, int K, int L, py::object fb, py::object mb, py::object nt, py::object f, py::object g, py::object llr, int device) {
+                 MK(PD_FASTSCLLUT); self->init(PD_FASTSCLLUT, N, K, 0, L, fb, nt, 0, NONE, f, g, llr, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("node_type"), arg("LUT_f"), arg("LUT_g"), arg("virtual_channel_llr"), arg("device") = 0);
+    // py_CASCLLUTDecoder.cpp:10-16
+    declare<PD_CASCLLUT>(m, "CASCLLUTDecoder", "CRC Aided Successive Cancellation List Decoder Using LUT", "channel_quantized_symbols")
+        .def(py::init([](int N, int K, int A, int L, py::object fb, py::object mb, int crc_n, py::object crc_p, py::object f, py::object g, py::object llr, int device) {
+                 MK(PD_CASCLLUT); self->init(PD_CASCLLUT, N, K, A, L, fb, NONE, crc_n, crc_p, f, g, llr, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("A"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("crc_n"), arg("crc_p"), arg("LUT_f"), arg("LUT_g"), arg("virtual_channel_llr"), arg("device") = 0);
+    // py_CAFastSCLLUTDecoder.cpp:11-15
+    declare<PD_CAFASTSCLLUT>(m, "CAFastSCLLUTDecoder", "CRC Aided Fast Successive Cancellation List Decoder Using LUT", "channel_quantized_symbols")
+        .def(py::init([](int N, int K, int A, int L, py::object fb, py::object mb, py::object nt, py::object f, py::object g, py::object llr, int device) {
+                 MK(PD_CAFASTSCLLUT); self->init(PD_CAFASTSCLLUT, N, K, A, L, fb, nt, 0, NONE, f, g, llr, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("A"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("node_type"), arg("LUT_f"), arg("LUT_g"), arg("virtual_channel_llr"), arg("device") = 0);
+    // py_SCUniformDecoder.cpp:10-15
+    declare<PD_SC_UNIFORM>(m, "SCUniformQuantizedDecoder", "Uniformly Quantized Successive Cancellation Decoder", "llr")
+        .def(py::init([](int N, int K, py::object fb, py::object mb, py::object rf, py::object rg, int v, int device) {
+                 MK(PD_SC_UNIFORM); self->init(PD_SC_UNIFORM, N, K, 0, 1, fb, NONE, 0, NONE, NONE, NONE, NONE, rf, rg, v, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("frozen_bits"), arg("message_bits"), arg("decoder_r_f"), arg("decoder_r_g"), arg("v"), arg("device") = 0);
+    // py_SCLUniformQuantizedDecoder.cpp:11-16
+    declare<PD_SCL_UNIFORM>(m, "SCLUniformQuantizedDecoder", "Uniformly Quantized Successive Cancellation List Decoder", "llr")
+        .def(py::init([](int N, int K, int L, py::object fb, py::object mb, py::object rf, py::object rg, int v, int device) {
+                 MK(PD_SCL_UNIFORM); self->init(PD_SCL_UNIFORM, N, K, 0, L, fb, NONE, 0, NONE, NONE, NONE, NONE, rf, rg, v, NONE, NONE, NONE, NONE, device); return self; }),
+             arg("N"), arg("K"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("decoder_r_f"), arg("decoder_r_g"), arg("v"), arg("device") = 0);
+    // py_SCLloydQuantizedDecoder.cpp:11-18
+    declare<PD_SC_LLOYD>(m, "SCLloydQuantizedDecoder", "Lloyd Quantized Successive Cancellation Decoder", "llr")
+        .def(py::init([](int N, int K, py::object fb, py::object mb, py::object bf, py::object bg, py::object rf, py::object rg, int v, int device) {
+                 MK(PD_SC_LLOYD); self->init(PD_SC_LLOYD, N, K, 0, 1, fb, NONE, 0, NONE, NONE, NONE, NONE, NONE, NONE, v, bf, bg, rf, rg, device); return self; }),
+             arg("N"), arg("K"), arg("frozen_bits"), arg("message_bits"), arg("boundaries_f"), arg("boundaries_g"), arg("reconstruction_f"), arg("reconstruction_g"), arg("v"), arg("device") = 0);
+    // py_SCLLloydQuantizedDecoder.cpp:11-18
+    declare<PD_SCL_LLOYD>(m, "SCLLloydQuantizedDecoder", "Lloyd Quantized Successive Cancellation List Decoder", "llr")
+        .def(py::init([](int N, int K, int L, py::object fb, py::object mb, py::object bf, py::object bg, py::object rf, py::object rg, int v, int device) {
+                 MK(PD_SCL_LLOYD); self->init(PD_SCL_LLOYD, N, K, 0, L, fb, NONE, 0, NONE, NONE, NONE, NONE, NONE, NONE, v, bf, bg, rf, rg, device); return self; }),
+             arg("N"), arg("K"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("boundaries_f"), arg("boundaries_g"), arg("reconstruction_f"), arg("reconstruction_g"), arg("v"), arg("device") = 0);
+#undef MK
+}

@@ -1,0 +1,180 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA decoders, called through the pybind11 mirror of the
+reference API and through the C ABI, against (a) the committed golden vectors produced by the compiled
+reference and (b) the CPU oracle on larger seeded batches.  Bit-exact for every class on these inputs; for the
+float family the stated tolerance of BASELINE.json (fp-tie frames <= 1e-6, PM within 1e-5 relative) is checked
+explicitly in test_float_path_metrics."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import common
+from golden.cases import CASES
+from oracle import polar_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def q():
+    import quantized_decoder_polar_codes_b200 as q
+    return q
+
+
+def _build(q, kind, kw):
+    return getattr(q, kind)(**kw)
+
+
+@pytest.mark.parametrize("cid,ckw", CASES, ids=[c[0] for c in CASES])
+def test_cuda_matches_golden(q, golden, cid, ckw):
+    ckw = dict(ckw)
+    kind = ckw.pop("kind")
+    kw, x, _ = common.make_case(kind, **ckw)
+    shape = tuple(golden[cid + "/shape"])
+    want = np.unpackbits(golden[cid + "/out"], axis=1)[:, : shape[1]]
+    dec = _build(q, kind, kw)
+    got = dec.decode(x)
+    assert got.shape == shape and got.dtype == np.uint8
+    bad = int((got != want).any(axis=1).sum())
+    assert bad == 0, f"{bad}/{shape[0]} frames differ from the reference ({dec.kernel})"
+
+
+BIG = [
+    ("SCDecoder", dict(N=128, K=64, B=4000)),
+    ("FastSCDecoder", dict(N=256, K=128, B=4000)),
+    ("SCLDecoder", dict(N=128, K=64, L=8, B=1500)),
+    ("FastSCLDecoder", dict(N=128, K=64, L=8, B=1500)),
+    ("CASCLDecoder", dict(N=128, K=64, L=8, A=40, B=1500)),
+    ("SCLUTDecoder", dict(N=128, K=32, B=4000)),
+    ("FastSCLUTDecoder", dict(N=256, K=128, B=4000)),
+    ("SCLLUTDecoder", dict(N=128, K=32, L=8, B=3000)),
+    ("SCLLUTDecoder", dict(N=128, K=64, L=2, B=1500)),
+    ("SCLLUTDecoder", dict(N=128, K=64, L=4, B=1500)),
+    ("SCLLUTDecoder", dict(N=64, K=32, L=5, B=1000)),
+    ("SCLLUTDecoder", dict(N=256, K=128, L=16, B=300)),
+    ("FastSCLLUTDecoder", dict(N=256, K=128, L=8, B=1500)),
+    ("FastSCLLUTDecoder", dict(N=512, K=300, L=8, B=300)),
+    ("CASCLLUTDecoder", dict(N=128, K=64, L=8, A=40, B=1500)),
+    ("CAFastSCLLUTDecoder", dict(N=256, K=128 + 24, L=8, A=128, B=1000)),
+    ("SCUniformQuantizedDecoder", dict(N=128, K=64, B=3000)),
+    ("SCLUniformQuantizedDecoder", dict(N=128, K=64, L=8, B=1000)),
+    ("SCLloydQuantizedDecoder", dict(N=128, K=64, B=3000)),
+    ("SCLLloydQuantizedDecoder", dict(N=128, K=64, L=8, B=1000)),
+    ("SCLLUTDecoder", dict(N=1024, K=512, L=8, B=300)),
+    ("SCLUTDecoder", dict(N=1024, K=512, B=1000)),
+    ("CAFastSCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, B=200)),
+]
+
+
+@pytest.mark.parametrize("kind,ckw", BIG, ids=[f"{k}-N{c['N']}-L{c.get('L', 1)}" for k, c in BIG])
+@pytest.mark.parametrize("tables", ["random", "working"])
+def test_cuda_matches_oracle(q, kind, ckw, tables):
+    t = "random" if tables == "random" else ("minsum" if "LUT" in kind else "channel")
+    kw, x, _ = common.make_case(kind, seed=77, tables=t, ebn0_db=1.0, **ckw)
+    want = po.OracleDecoder(kind, **kw).decode(x)
+    dec = _build(q, kind, kw)
+    got = dec.decode(x)
+    bad = int((got != want).any(axis=1).sum())
+    assert bad == 0, f"{bad}/{x.shape[0]} frames differ from the oracle ({dec.kernel})"
+
+
+def test_reference_call_conventions(q):
+    """(N,), (1,N), float64 symbols (forcecast like py::array_t<int>), uint8 fast path, batch of one."""
+    kw, x, _ = common.make_case("SCLLUTDecoder", N=128, K=32, L=8, B=8, seed=3)
+    want = po.OracleDecoder("SCLLUTDecoder", **kw).decode(x)
+    dec = q.SCLLUTDecoder(**kw)
+    y1 = dec.decode(x[0])
+    assert y1.shape == (32,) and (y1 == want[0]).all()
+    assert (dec.decode(x[0][None, :]) == want[0]).all() and dec.decode(x[0][None, :]).shape == (32,)
+    assert (dec.decode(x[1].astype(np.float64)) == want[1]).all()           # ProbabilityDomain driver passes float64
+    assert (dec.decode(channel_quantized_symbols=x[2].tolist()) == want[2]).all()
+    assert (dec.decode(x.astype(np.uint8)) == want).all()
+    kwf, xf, _ = common.make_case("SCDecoder", N=128, K=64, B=4, seed=4)
+    wantf = po.OracleDecoder("SCDecoder", **kwf).decode(xf)
+    decf = q.SCDecoder(**kwf)
+    assert (decf.decode(llr=xf[0][None, :]) == wantf[0]).all()              # mainFPDecoder.py passes (1,N) float64
+    assert (decf.decode(xf.astype(np.float32)) == po.OracleDecoder("SCDecoder", **kwf).decode(xf.astype(np.float32).astype(np.float64))).all()
+
+
+def test_out_of_range_symbol_is_an_error(q):
+    kw, x, _ = common.make_case("SCLUTDecoder", N=64, K=32, B=4, seed=3)
+    dec = q.SCLUTDecoder(**kw)
+    x = x.copy()
+    x[2, 5] = 16
+    with pytest.raises(ValueError, match="outside the root lookup table"):
+        dec.decode(x)
+    x[2, 5] = 3
+    dec.decode(x)  # decoder stays usable
+
+
+def test_bad_tables_are_rejected(q):
+    kw, x, _ = common.make_case("SCLUTDecoder", N=64, K=32, B=4, seed=3)
+    f = [np.array(t) for t in kw["LUT_f"]]
+    f[5][0, 2, 3] = 16
+    kw2 = dict(kw, LUT_f=f)
+    with pytest.raises(ValueError, match="consumer alphabet"):
+        q.SCLUTDecoder(**kw2)
+
+
+def test_float_path_metrics(q):
+    """BASELINE.json: float decoders must match decoded bits except fp-tie frames (<=1e-6 of frames) and path
+    metrics within 1e-5 relative.  Our fp64 kernels evaluate the reference's expressions in the reference's
+    order, so both hold with zero slack on these inputs; the tolerance is still the stated one."""
+    import torch
+    from quantized_decoder_polar_codes_b200 import capi
+    for kind in ["SCLDecoder", "FastSCLDecoder", "SCLUniformQuantizedDecoder", "SCLLUTDecoder"]:
+        kw, x, _ = common.make_case(kind, N=256, K=128, L=8, B=500, seed=9, tables="minsum" if "LUT" in kind else "channel", ebn0_db=1.0)
+        want, pm_want, win_want = po.OracleDecoder(kind, **kw).decode(x, return_pm=True)
+        dec = _build(q, kind, kw)
+        lut = "LUT" in kind
+        xin = torch.from_numpy(x.astype(np.uint8) if lut else x.astype(np.float64)).cuda()
+        out = torch.empty((x.shape[0], 128), dtype=torch.uint8, device="cuda")
+        pm = torch.zeros((x.shape[0], 8), dtype=torch.float64, device="cuda")
+        win = torch.zeros(x.shape[0], dtype=torch.int32, device="cuda")
+        capi.check(capi.lib().pd_set_debug_outputs(dec._handle, pm.data_ptr(), win.data_ptr()))
+        stream = torch.cuda.current_stream().cuda_stream
+        capi.decode_device(dec, xin.data_ptr(), capi.PD_U8 if lut else capi.PD_F64, x.shape[0], out.data_ptr(), stream)
+        capi.sync_check(dec, stream)
+        capi.check(capi.lib().pd_set_debug_outputs(dec._handle, None, None))
+        got = out.cpu().numpy()
+        mism = (got != want).any(axis=1).mean()
+        assert mism <= 1e-6
+        pmg = pm.cpu().numpy()
+        fin = np.isfinite(pm_want) & (np.abs(pm_want) < 1e299)
+        assert np.allclose(pmg[fin], pm_want[fin], rtol=1e-5, atol=0)
+        assert (win.cpu().numpy() == win_want).all()
+
+
+def test_error_counters(q):
+    import torch
+    from quantized_decoder_polar_codes_b200 import capi
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 2, (1000, 37), dtype=np.uint8)
+    b = a.copy()
+    flips = rng.random(a.shape) < 0.01
+    b[flips] ^= 1
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    capi.check(capi.lib().pd_count_errors(ta.data_ptr(), tb.data_ptr(), 1000, 37, cnt.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert cnt.cpu().tolist() == [int(flips.sum()), int(flips.any(axis=1).sum())]
+
+
+def test_properties_at_full_size(q):
+    """North-star shape at a batch the oracle cannot follow: size-independent properties.
+    (1) decoding is per-frame independent: any sub-batch / permutation gives the same rows;
+    (2) high-SNR frames decode to the transmitted word (encode -> channel -> decode round trip);
+    (3) SCL with L=1 equals SC wherever no LLR is exactly zero-tied (here: identical decisions on clean frames)."""
+    kw, x, truth = common.make_case("SCLLUTDecoder", N=1024, K=512, L=8, B=20000, seed=123, tables="minsum", ebn0_db=3.5)
+    dec = q.SCLLUTDecoder(**kw)
+    xb = x.astype(np.uint8)
+    y = dec.decode(xb)
+    assert y.shape == (20000, 512)
+    perm = np.random.default_rng(1).permutation(20000)
+    assert (dec.decode(xb[perm]) == y[perm]).all()
+    assert (dec.decode(xb[:777]) == y[:777]).all()
+    bler = (y != truth).any(axis=1).mean()
+    assert bler < 0.05, bler
+    sub = np.arange(0, 20000, 400)
+    want = po.OracleDecoder("SCLLUTDecoder", **kw).decode(x[sub])
+    assert (y[sub] == want).all()
