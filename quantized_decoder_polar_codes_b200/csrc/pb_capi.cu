@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -90,6 +91,7 @@ struct pd_decoder {
     size_t ws_user_cap = 0;
     StreamSlot slot[2];
     int64_t chunk_frames = 0;
+    bool force_generic = false;
 };
 
 namespace {
@@ -226,7 +228,7 @@ int build_lut(pd_decoder *D, const pd_config *c) {
     if ((rc = upload(D, tabs, &D->dev.tabs))) return rc;
     if ((rc = upload(D, llr, &D->dev.llr))) return rc;
     if ((rc = upload(D, loff, &D->dev.llr_off))) return rc;
-    plan_fast_lut(D->dev, D->steps, tabs, pool, c->frozen_bits, &D->fast);
+    plan_fast_lut(D->dev, PD_SCLUT, PD_SCLLUT, PD_CASCLLUT, tabs, pool, llr, loff, c->llr_off, c->frozen_bits, D->dev.crc_taps, &D->fast);
     return PD_OK;
 }
 
@@ -294,11 +296,13 @@ int plan_generic(pd_decoder *D) {
     return PD_OK;
 }
 
-bool want_fast(const pd_decoder *D, int dtype) { return D->fast.ok && dtype != PD_F64; }
+bool want_fast(const pd_decoder *D, int dtype, const void *d_in) {
+    return D->fast.ok && dtype != PD_F64 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && !D->force_generic;
+}
 
 int launch(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws) {
     if (B <= 0) return PD_OK;
-    if (want_fast(D, dtype)) {
+    if (want_fast(D, dtype, d_in)) {
         int rc = launch_fast_lut(D->dev, D->fast, d_in, dtype, B, d_out, s, D->d_err, D->dbg_pm, D->dbg_win, D->sm_count);
         g_launches++;
         if (rc != 0) return fail(PD_ECUDA, "fast kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -438,7 +442,8 @@ int pd_create(const pd_config *c, pd_decoder **out) {
         cudaMemset(p, 0, sizeof(int));
     }
     if ((rc = plan_generic(D))) return bail(rc);
-    D->kernel_name = D->fast.ok ? D->fast.name : "generic";
+    if (const char *e = getenv("POLAR_B200_FORCE_GENERIC")) D->force_generic = e[0] == '1';
+    D->kernel_name = (D->fast.ok && !D->force_generic) ? D->fast.name : "generic";
     // frames per pipeline chunk of pd_decode: ~32 MB of input per chunk
     size_t in_frame = (size_t)N * (d.domain == DOM_LUT ? 4 : 8);
     D->chunk_frames = std::max<int64_t>(1024, (int64_t)((32u << 20) / in_frame));
@@ -472,7 +477,7 @@ int pd_decode_device(pd_decoder *D, const void *dev_in, int in_dtype, int64_t B,
     CUDA_TRY(cudaSetDevice(D->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
     char *ws = nullptr;
-    if (!want_fast(D, in_dtype) && !D->use_smem) {
+    if (!want_fast(D, in_dtype, dev_in) && !D->use_smem) {
         size_t need = D->ws_bytes * (size_t)generic_grid(D, B);
         if (need > D->ws_user_cap) {
             CUDA_TRY(cudaDeviceSynchronize());
@@ -507,7 +512,7 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
     CUDA_TRY(cudaSetDevice(D->device));
     const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
     const int64_t chunk = std::min<int64_t>(B, D->chunk_frames);
-    const bool need_ws = !want_fast(D, in_dtype) && !D->use_smem;
+    const bool need_ws = !D->use_smem;
     for (auto &sl : D->slot) {
         if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         size_t in_need = (size_t)chunk * N * esz, out_need = (size_t)chunk * Ko;

@@ -78,6 +78,19 @@ def test_cuda_matches_oracle(q, kind, ckw, tables):
     assert bad == 0, f"{bad}/{x.shape[0]} frames differ from the oracle ({dec.kernel})"
 
 
+@pytest.mark.parametrize("kind,ckw", [b for b in BIG if b[0] in ("SCLUTDecoder", "SCLLUTDecoder", "CASCLLUTDecoder")][:6],
+                         ids=lambda v: v if isinstance(v, str) else f"N{v['N']}-L{v.get('L', 1)}")
+def test_generic_kernel_still_covers_the_fast_kernels_classes(q, kind, ckw, monkeypatch):
+    """The specialised warp kernel takes over the LUT SC/SCL classes; the schedule-driven generic kernel must
+    stay bit-exact on them too (it is what runs for table shapes the specialised kernel does not accept)."""
+    monkeypatch.setenv("POLAR_B200_FORCE_GENERIC", "1")
+    kw, x, _ = common.make_case(kind, seed=78, **ckw)
+    dec = _build(q, kind, kw)
+    assert dec.kernel == "generic"
+    want = po.OracleDecoder(kind, **kw).decode(x)
+    assert (dec.decode(x) == want).all()
+
+
 def test_reference_call_conventions(q):
     """(N,), (1,N), float64 symbols (forcecast like py::array_t<int>), uint8 fast path, batch of one."""
     kw, x, _ = common.make_case("SCLLUTDecoder", N=128, K=32, L=8, B=8, seed=3)
