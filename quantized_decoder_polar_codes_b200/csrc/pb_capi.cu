@@ -296,6 +296,7 @@ int plan_generic(pd_decoder *D) {
     return PD_OK;
 }
 
+size_t ws_need(const pd_decoder *D, int dtype, const void *d_in, int64_t B);
 bool want_fast(const pd_decoder *D, int dtype, const void *d_in) {
     return D->fast.ok && dtype != PD_F64 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && !D->force_generic;
 }
@@ -303,12 +304,18 @@ bool want_fast(const pd_decoder *D, int dtype, const void *d_in) {
 int launch(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws) {
     if (B <= 0) return PD_OK;
     if (want_fast(D, dtype, d_in)) {
-        int rc = launch_fast_lut(D->dev, D->fast, d_in, dtype, B, d_out, s, D->d_err, D->dbg_pm, D->dbg_win, D->sm_count);
+        int rc = launch_fast_lut(D->dev, D->fast, d_in, dtype, B, d_out, s, reinterpret_cast<uint32_t *>(ws), D->d_err, D->dbg_pm, D->dbg_win, D->sm_count);
         g_launches++;
         if (rc != 0) return fail(PD_ECUDA, "fast kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         return PD_OK;
     }
     return launch_generic(D, d_in, dtype, B, d_out, s, ws);
+}
+
+// bytes of global workspace the kernel chosen for this call needs
+size_t ws_need(const pd_decoder *D, int dtype, const void *d_in, int64_t B) {
+    if (want_fast(D, dtype, d_in)) return D->fast.ws_bytes_per_cta * (size_t)fast_grid(D->fast, B, D->sm_count);
+    return D->use_smem ? 0 : D->ws_bytes * (size_t)generic_grid(D, B);
 }
 
 size_t dtype_size(int t) { return t == PD_U8 ? 1 : t == PD_I32 ? 4 : 8; }
@@ -477,8 +484,7 @@ int pd_decode_device(pd_decoder *D, const void *dev_in, int in_dtype, int64_t B,
     CUDA_TRY(cudaSetDevice(D->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
     char *ws = nullptr;
-    if (!want_fast(D, in_dtype, dev_in) && !D->use_smem) {
-        size_t need = D->ws_bytes * (size_t)generic_grid(D, B);
+    if (size_t need = ws_need(D, in_dtype, dev_in, B)) {
         if (need > D->ws_user_cap) {
             CUDA_TRY(cudaDeviceSynchronize());
             cudaFree(D->ws_user);
@@ -512,16 +518,14 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
     CUDA_TRY(cudaSetDevice(D->device));
     const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
     const int64_t chunk = std::min<int64_t>(B, D->chunk_frames);
-    const bool need_ws = !D->use_smem;
     for (auto &sl : D->slot) {
         if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         size_t in_need = (size_t)chunk * N * esz, out_need = (size_t)chunk * Ko;
         if (sl.in_cap < in_need) { cudaFree(sl.d_in); sl.d_in = nullptr; sl.in_cap = 0; CUDA_TRY(cudaMalloc(&sl.d_in, in_need)); sl.in_cap = in_need; }
         if (sl.out_cap < out_need) { cudaFree(sl.d_out); sl.d_out = nullptr; sl.out_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.d_out, out_need)); sl.out_cap = out_need; }
-        if (need_ws) {
-            size_t ws_need = D->ws_bytes * (size_t)generic_grid(D, chunk);
-            if (sl.ws_cap < ws_need) { cudaFree(sl.ws); sl.ws = nullptr; sl.ws_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.ws, ws_need)); sl.ws_cap = ws_need; }
-        }
+        // our own staging buffers are cudaMalloc'ed (256-B aligned), so the kernel choice depends on the dtype only
+        size_t wsn = std::max(ws_need(D, in_dtype, nullptr, chunk), (size_t)16);
+        if (sl.ws_cap < wsn) { cudaFree(sl.ws); sl.ws = nullptr; sl.ws_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.ws, wsn)); sl.ws_cap = wsn; }
     }
     int which = 0;
     for (int64_t f0 = 0; f0 < B; f0 += chunk, which ^= 1) {

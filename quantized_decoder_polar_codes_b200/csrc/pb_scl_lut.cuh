@@ -30,18 +30,19 @@
 
 namespace pb {
 
-constexpr int kRing = 16;          // ring slots per lane; kRing-1 lines in flight
+constexpr int kRingChunks = 4;     // ring slots per lane, 4 lines (16 bytes per lane) each; 3 chunks in flight
 constexpr unsigned kFull = 0xffffffffu;
 
 struct FastParams {
-    const uint32_t *stream;        // upper-level table stream, 32 words per line
-    const uint32_t *bundles;       // [N/8][8][32 lanes][4] words: the 29 lines of each 8-leaf subtree, lane-transposed
-    int n_lines;
+    const uint32_t *stream;        // table stream in consumption order: [chunk][lane][4 lines' word of that lane]
+    int n_chunks;
     const uint32_t *frozen_words;  // frozen mask, 32 leaves per word
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
-    int vwords, xwords, inwords;
-    int voff[kMaxLog + 2];
+    int vwords, xwords, scrwords;  // shared-memory words per lane: value levels gl+1..top, X; scratch words per warp
+    int gl;                        // value levels 1..gl live in the global (L2-resident) workspace, the rest in shared memory
+    int gwords;                    // workspace words per lane
+    int voff[kMaxLog + 2];         // word offset of level d inside its home (workspace for d<=gl, shared memory above)
 };
 
 struct FastPlan {
@@ -51,13 +52,14 @@ struct FastPlan {
     bool ca = false;
     FastParams p{};
     size_t smem = 0;
+    size_t ws_bytes_per_cta = 0;
     int ctas_per_sm = 0;
     std::vector<void *> allocs;
 };
 
-__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc) {
+__device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint4 *gsrc) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
     asm volatile("cp.async.commit_group;\n" ::);
 }
 template <int NPEND>
@@ -73,7 +75,7 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x) {
 template <int LOGL, bool CA>
 __global__ void __launch_bounds__(32)
 scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastParams fp, const void *__restrict__ in, int in_dtype,
-                    uint8_t *__restrict__ out, long long B, int *err_flag, double *dbg_pm, int *dbg_win) {
+                    uint8_t *__restrict__ out, long long B, uint32_t *__restrict__ ws, int *err_flag, double *dbg_pm, int *dbg_win) {
     constexpr int L = 1 << LOGL;
     constexpr int FPW = 32 / L;
     extern __shared__ __align__(16) uint32_t sm[];
@@ -81,39 +83,36 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     const int grp = lane >> LOGL, me = lane & (L - 1), gbase = lane & ~(L - 1);
     const int N = d.N, n = d.n;
     const int NS = N >> 3;          // number of 8-leaf subtrees
-    const int top = n - 3;          // depth of the subtree roots = deepest level kept in shared memory
+    const int top = n - 3;          // depth of the subtree roots = deepest value level kept in memory
 
-    uint32_t *V = sm;
-    uint32_t *X = V + fp.vwords * 32;
-    uint32_t *IN = X + fp.xwords * 32;
-    uint32_t *RING = IN + fp.inwords * FPW;
-    double *KS = reinterpret_cast<double *>(RING + kRing * 32);      // [32][2]
-    uint32_t *SEL = reinterpret_cast<uint32_t *>(KS + 64);           // [32]
+    uint32_t *V = sm;                                  // value levels gl+1..top, [word][lane]
+    uint32_t *X = V + fp.vwords * 32;                  // partial sums, in place, [word][lane]
+    uint32_t *SCR = X + fp.xwords * 32;                // epilogue scratch [word][frame in warp] (L > 1)
+    uint32_t *RING = SCR + fp.scrwords;                // [kRingChunks][lane][4]
+    uint32_t *G = ws + (size_t)blockIdx.x * fp.gwords * 32;   // value levels 1..gl, [word][lane], L2-resident
+    double *KS = reinterpret_cast<double *>(RING + kRingChunks * 128);   // [32][2]
+    uint32_t *SEL = reinterpret_cast<uint32_t *>(KS + 64);               // [32]
 
-    // ---- upper-level table stream: private ring per lane (lane l only ever touches word l of a line) ----
-    int fetch_pos = 0;      // stream position of the next line to prefetch
-    unsigned line_no = 0;   // lines consumed so far (ring slot = line_no & 15)
-    for (int i = 0; i < kRing - 1; ++i) {
-        cp_async4(&RING[i * 32 + lane], fp.stream + (size_t)fetch_pos * 32 + lane);
-        fetch_pos = (fetch_pos + 1 == fp.n_lines) ? 0 : fetch_pos + 1;
-    }
-    auto next_line = [&]() -> uint32_t {
-        cp_async_wait<kRing - 2>();
-        uint32_t v = RING[(line_no & (kRing - 1)) * 32 + lane];
-        cp_async4(&RING[((line_no + kRing - 1) & (kRing - 1)) * 32 + lane], fp.stream + (size_t)fetch_pos * 32 + lane);
-        fetch_pos = (fetch_pos + 1 == fp.n_lines) ? 0 : fetch_pos + 1;
-        ++line_no;
-        return v;
+    // ---- table stream.  Every f/g table (one 128-byte line = 16x16 nibbles) and every leaf LLR row (16 doubles)
+    //      is consumed exactly once per pass, in a fixed order, and lane l only ever needs word l of a line.  The
+    //      host lays the lines out in consumption order, 4 lines per lane-transposed 512-byte chunk, and each
+    //      lane streams ITS 16 bytes of every chunk with cp.async into a private ring (no cross-lane sync). ----
+    int fetch_chunk = 0;    // stream position of the next chunk to prefetch
+    unsigned line_no = 0;   // lines consumed so far
+    const uint4 *stream4 = reinterpret_cast<const uint4 *>(fp.stream) + lane;
+    auto issue_chunk = [&](int slot) {
+        cp_async16(&RING[slot * 128 + lane * 4], stream4 + (size_t)fetch_chunk * 32);
+        fetch_chunk = (fetch_chunk + 1 == fp.n_chunks) ? 0 : fetch_chunk + 1;
     };
-    // ---- bottom-subtree bundles: 32 lines (29 used) per 8-leaf subtree, lane-transposed so that 8 LDG.128 per
-    //      lane fetch the lane's word of every line; double buffered in registers one subtree ahead ----
-    auto load_bundle = [&](uint32_t (&tb)[32], int sidx) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(fp.bundles) + (size_t)sidx * 256 + lane;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint4 v = __ldg(src + j * 32);
-            tb[4 * j] = v.x; tb[4 * j + 1] = v.y; tb[4 * j + 2] = v.z; tb[4 * j + 3] = v.w;
+    for (int i = 0; i < kRingChunks - 1; ++i) issue_chunk(i);
+    auto next_line = [&]() -> uint32_t {
+        const unsigned q = line_no & 3u, slot = (line_no >> 2) & (kRingChunks - 1);
+        if (q == 0) {
+            issue_chunk((slot + kRingChunks - 1) & (kRingChunks - 1));   // refill the chunk consumed before this one
+            cp_async_wait<kRingChunks - 1>();                            // ... and make sure this one has landed
         }
+        ++line_no;
+        return RING[slot * 128 + lane * 4 + q];
     };
     auto lut16 = [&](uint32_t treg, uint32_t a, uint32_t b) -> uint32_t {
         const uint32_t w = __shfl_sync(kFull, treg, a * 2 + (b >> 3));
@@ -121,44 +120,32 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     };
     auto nib = [](uint32_t w, int k) -> uint32_t { return (w >> (4 * k)) & 15u; };
 
-    uint32_t bufA[32], bufB[32];
-    load_bundle(bufA, 0);
-
-    const unsigned gmask_below = (L == 32 ? kFull : (((1u << L) - 1u) << gbase)) & ((1u << lane) - 1u);
-
     const long long n_groups = (B + FPW - 1) / FPW;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        // ---- stage the channel symbols of the FPW frames as nibbles: IN[w*FPW + frame_in_warp] ----
-        for (int fi = 0; fi < FPW; ++fi) {
-            long long frame = g * FPW + fi;
-            if (frame >= B) frame = B - 1;
-            for (int c = lane; c < N / 16; c += 32) {
-                uint32_t x0, x1, x2, x3;
-                bool bad = false;
-                if (in_dtype == 0) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(in) + (size_t)frame * N) + c);
-                    x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
-                } else {
-                    const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const int32_t *>(in) + (size_t)frame * N) + c * 4;
-                    auto ld4 = [&](int q) -> uint32_t {
-                        const uint4 v = __ldg(p + q);
-                        bad |= ((v.x | v.y | v.z | v.w) & 0xffffff00u) != 0;
-                        return (v.x & 0xff) | ((v.y & 0xff) << 8) | ((v.z & 0xff) << 16) | ((v.w & 0xff) << 24);
-                    };
-                    x0 = ld4(0); x1 = ld4(1); x2 = ld4(2); x3 = ld4(3);
-                }
-                const uint32_t bound = (c * 16 < N / 2) ? (uint32_t)d.root_qa : (uint32_t)d.root_qb;
-                auto chk = [&](uint32_t x) {
-#pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) bad |= ((x >> (8 * bb)) & 0xffu) >= bound;
-                };
-                chk(x0); chk(x1); chk(x2); chk(x3);
-                if (bad) { *err_flag = 1; x0 = x1 = x2 = x3 = 0; }
-                IN[(2 * c) * FPW + fi] = pack4(x0) | (pack4(x1) << 16);
-                IN[(2 * c + 1) * FPW + fi] = pack4(x2) | (pack4(x3) << 16);
+        long long my_frame = g * FPW + grp;
+        if (my_frame >= B) my_frame = B - 1;
+        // 8 channel symbols (one output word's worth of the a- or b-half) -> 8 nibbles, with the range check the
+        // reference does not have (an out-of-range symbol indexes past the root table there)
+        auto in8 = [&](int sym0) -> uint32_t {
+            uint32_t x0, x1;
+            bool bad = false;
+            if (in_dtype == 0) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(in) + (size_t)my_frame * N + sym0));
+                x0 = v.x; x1 = v.y;
+            } else {
+                const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const int32_t *>(in) + (size_t)my_frame * N + sym0);
+                const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+                bad = ((v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) & 0xffffff00u) != 0;
+                x0 = (v0.x & 0xff) | ((v0.y & 0xff) << 8) | ((v0.z & 0xff) << 16) | ((v0.w & 0xff) << 24);
+                x1 = (v1.x & 0xff) | ((v1.y & 0xff) << 8) | ((v1.z & 0xff) << 16) | ((v1.w & 0xff) << 24);
             }
-        }
-        __syncwarp();
+            const uint32_t bound = (sym0 < N / 2) ? (uint32_t)d.root_qa : (uint32_t)d.root_qb;
+            // every byte < bound  <=>  no byte of (x + (128-bound)) has its top bit set, given x < 128 per byte
+            const uint32_t addc = 0x01010101u * (128u - bound);
+            bad |= (((x0 | x1) & 0x80808080u) != 0) || ((((x0 & 0x7f7f7f7fu) + addc) | ((x1 & 0x7f7f7f7fu) + addc)) & 0x80808080u) != 0;
+            if (bad) { *err_flag = 1; x0 = x1 = 0; }
+            return pack4(x0) | (pack4(x1) << 16);
+        };
 
         double PM = (me == 0) ? 0.0 : d.pm_init;
         // 3-bit-per-level slot pointers for levels 1..top: values (pv) and left-child partial sums (pu)
@@ -167,36 +154,54 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         auto setown = [&](uint32_t &pw, int lev) { pw = (pw & ~(7u << (3 * (lev - 1)))) | ((uint32_t)me << (3 * (lev - 1))); };
         auto vslot = [&](int lev) -> int { return L == 1 ? lane : (gbase | getp(pv, lev)); };
         auto uslot = [&](int lev) -> int { return L == 1 ? lane : (gbase | getp(pu, lev)); };
+        // home of value level `lev` (1..top) for slot lane `sl`: word w is at ptr[w*32]
+        auto level_ptr = [&](int lev, int sl) -> uint32_t * {
+            return (lev <= fp.gl ? G : V) + fp.voff[lev] * 32 + sl;
+        };
 
         // f / g step at depth dd (<= top-1): level dd -> level dd+1 (>= 8 symbols), written to the lane's own slot
-        auto fg_step = [&](int dd, uint32_t node, auto isg_c) {
-            constexpr bool ISG = decltype(isg_c)::value;
+        auto fg_step = [&](int dd, uint32_t node, bool isg) {
             const int ct = N >> (dd + 1);
             const uint32_t t0 = next_line();
-            uint32_t t1 = 0;
-            if (ISG) t1 = next_line();
-            const uint32_t *src;
-            int sstride;
-            if (dd == 0) { src = IN + grp; sstride = FPW; }
-            else { src = V + fp.voff[dd] * 32 + vslot(dd); sstride = 32; }
-            uint32_t *dst = V + fp.voff[dd + 1] * 32 + lane;
+            uint32_t t1 = t0;
+            if (isg) t1 = next_line();
+            const uint32_t *src = (dd == 0) ? nullptr : level_ptr(dd, vslot(dd));
+            uint32_t *dst = level_ptr(dd + 1, lane);
             const uint32_t *xsrc = X + uslot(dd + 1);
             const uint32_t ub0 = (2u * node) * (uint32_t)ct;
             const int nw = ct >> 3;
+            auto getA = [&](int w) -> uint32_t { return dd == 0 ? in8(8 * w) : src[w * 32]; };
+            auto getB = [&](int w) -> uint32_t { return dd == 0 ? in8(N / 2 + 8 * w) : src[(nw + w) * 32]; };
+            auto getU = [&](int w) -> uint32_t {
+                if (!isg) return 0u;
+                const uint32_t bit = ub0 + 8u * w;
+                return xsrc[(bit >> 5) * 32] >> (bit & 31u);
+            };
+            // operands of word w+1 are fetched (possibly from L2) while word w is looked up
+            uint32_t A = getA(0), Bv = getB(0), ub = getU(0);
             for (int w = 0; w < nw; ++w) {
-                const uint32_t A = src[w * sstride], Bv = src[(nw + w) * sstride];
-                uint32_t ub = 0;
-                if (ISG) { const uint32_t bit = ub0 + 8u * w; ub = xsrc[(bit >> 5) * 32] >> (bit & 31u); }
+                uint32_t An = 0, Bn = 0, un = 0;
+                if (w + 1 < nw) { An = getA(w + 1); Bn = getB(w + 1); un = getU(w + 1); }
                 uint32_t o = 0;
+                if (!isg) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t a = (A >> (4 * k)) & 15u, b = (Bv >> (4 * k)) & 15u;
-                    const uint32_t sl = a * 2 + (b >> 3);
-                    uint32_t wv = __shfl_sync(kFull, t0, sl);
-                    if (ISG) { const uint32_t wv1 = __shfl_sync(kFull, t1, sl); wv = ((ub >> k) & 1u) ? wv1 : wv; }
-                    o |= ((wv >> ((b & 7u) * 4)) & 15u) << (4 * k);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t a = (A >> (4 * k)) & 15u, b = (Bv >> (4 * k)) & 15u;
+                        const uint32_t wv = __shfl_sync(kFull, t0, a * 2 + (b >> 3));
+                        o |= ((wv >> ((b & 7u) * 4)) & 15u) << (4 * k);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t a = (A >> (4 * k)) & 15u, b = (Bv >> (4 * k)) & 15u;
+                        const uint32_t sl = a * 2 + (b >> 3);
+                        const uint32_t wv0 = __shfl_sync(kFull, t0, sl), wv1 = __shfl_sync(kFull, t1, sl);
+                        const uint32_t wv = ((ub >> k) & 1u) ? wv1 : wv0;
+                        o |= ((wv >> ((b & 7u) * 4)) & 15u) << (4 * k);
+                    }
                 }
                 dst[w * 32] = o;
+                A = An; Bv = Bn; ub = un;
             }
             if (L > 1) setown(pv, dd + 1);
             __syncwarp();
@@ -233,144 +238,129 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         uint32_t w21 = 0;    // [15:0] 4 symbols of the depth top+1 node, [23:16] 2 symbols of the depth top+2 node
         uint32_t xb = 0;     // partial sums of the subtree, in place (bit i = leaf i)
 
-        // leaf decision (PD/src/SCLUTDecoder.cpp:59-67 / SCLLUTDecoder.cpp:92-145); sets bit `pos` of xb
-        auto leaf = [&](uint32_t phi, int pos, uint32_t sym, uint32_t lr, bool frozen) {
-            uint32_t bit = 0;
-            if (L == 1) {
-                if (!frozen) {
-                    const int lo_ = __shfl_sync(kFull, (int)lr, 2 * sym), hi_ = __shfl_sync(kFull, (int)lr, 2 * sym + 1);
-                    bit = (__hiloint2double(hi_, lo_) <= 0) ? 1u : 0u;
-                }
-            } else {
-                const int lo_ = __shfl_sync(kFull, (int)lr, 2 * sym), hi_ = __shfl_sync(kFull, (int)lr, 2 * sym + 1);
-                const double DM = __hiloint2double(hi_, lo_);
-                if (frozen) {
-                    PM += fabs(DM) * (double)(DM < 0);
-                } else {
-                    const uint32_t dec = (DM < 0) ? 1u : 0u;
-                    const double K0 = PM, K1 = PM + fabs(DM);
-                    __syncwarp();
-                    *reinterpret_cast<double2 *>(&KS[lane * 2]) = make_double2(K0, K1);
-                    // stable rank of (key, index) among the group's 2L keys == libstdc++ insertion sort for 2L <= 16
-                    int r0 = __popc(__match_any_sync(kFull, (unsigned long long)__double_as_longlong(K0)) & gmask_below);
-                    int r1 = __popc(__match_any_sync(kFull, (unsigned long long)__double_as_longlong(K1)) & gmask_below);
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < L; ++j) {
-                        const double2 kf = *reinterpret_cast<const double2 *>(&KS[(gbase + j) * 2]);
-                        r0 += (kf.x < K0) + (kf.y < K0);
-                        r1 += !(K1 < kf.x) + (kf.y < K1);
-                    }
-                    if (r0 < L) SEL[gbase + r0] = (uint32_t)me;
-                    if (r1 < L) SEL[gbase + r1] = (uint32_t)me | 16u;
-                    __syncwarp();
-                    const uint32_t s = SEL[lane];
-                    const int p = gbase | (int)(s & 15u);
-                    const uint32_t fl = s >> 4;
-                    PM = KS[p * 2 + fl];
-                    bit = __shfl_sync(kFull, dec, p) ^ fl;
-                    w3 = __shfl_sync(kFull, w3, p);
-                    w21 = __shfl_sync(kFull, w21, p);
-                    xb = __shfl_sync(kFull, xb, p);
-                    pv = __shfl_sync(kFull, pv, p);
-                    pu = __shfl_sync(kFull, pu, p);
-                }
-            }
-            xb = (xb & ~(1u << pos)) | (bit << pos);
-            (void)phi;
-        };
-
-        // one 8-leaf subtree, fully unrolled; tb = its bundle (line order = consumption order, see plan_fast_lut)
-        auto subtree8 = [&](int sidx, const uint32_t (&tb)[32]) {
-            const uint32_t fz = (__ldg(fp.frozen_words + (sidx >> 2)) >> ((sidx & 3) * 8)) & 0xffu;
-            w3 = V[fp.voff[top] * 32 + vslot(top)];
-            xb = 0;
-            // A.f : 8 -> 4 symbols
-            uint32_t w2 = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) w2 |= lut16(tb[0], nib(w3, k), nib(w3, k + 4)) << (4 * k);
-            w21 = w2;
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const int bl = 1 + 15 * m;
-                // B.f : 4 -> 2 symbols
-                {
-                    const uint32_t c2 = w21 & 0xffffu;
-                    const uint32_t w1 = lut16(tb[bl], nib(c2, 0), nib(c2, 2)) | (lut16(tb[bl], nib(c2, 1), nib(c2, 3)) << 4);
-                    w21 = c2 | (w1 << 16);
-                }
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int cl = bl + 1 + 7 * c, pos = 4 * m + 2 * c;
-                    const uint32_t phi = 8u * sidx + pos;
-                    {   // left leaf through the f table of the depth n-1 node
-                        const uint32_t w1 = w21 >> 16;
-                        const uint32_t sym = lut16(tb[cl], nib(w1, 0), nib(w1, 1));
-                        leaf(phi, pos, sym, tb[cl + 1], (fz >> pos) & 1u);
-                    }
-                    {   // right leaf through the g tables, u = left leaf's bit
-                        const uint32_t w1 = w21 >> 16;
-                        const uint32_t a = nib(w1, 0), b = nib(w1, 1);
-                        const uint32_t s0 = lut16(tb[cl + 2], a, b), s1 = lut16(tb[cl + 3], a, b);
-                        const uint32_t sym = ((xb >> pos) & 1u) ? s1 : s0;
-                        leaf(phi + 1, pos + 1, sym, tb[cl + 4], (fz >> (pos + 1)) & 1u);
-                    }
-                    xb ^= ((xb >> (pos + 1)) & 1u) << pos;    // combine of the depth n-1 node
-                    if (c == 0) {   // B.g : u = the 2 partial sums just formed
-                        const uint32_t c2 = w21 & 0xffffu;
-                        uint32_t w1 = 0;
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const uint32_t a = nib(c2, k), b = nib(c2, k + 2);
-                            const uint32_t s0 = lut16(tb[bl + 6], a, b), s1 = lut16(tb[bl + 7], a, b);
-                            w1 |= (((xb >> (pos + k)) & 1u) ? s1 : s0) << (4 * k);
-                        }
-                        w21 = c2 | (w1 << 16);
-                    }
-                }
-                xb ^= ((xb >> (4 * m + 2)) & 3u) << (4 * m);    // combine of the depth n-2 node
-                if (m == 0) {   // A.g : u = the 4 partial sums of the left half
-                    uint32_t w2g = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t a = nib(w3, k), b = nib(w3, k + 4);
-                        const uint32_t s0 = lut16(tb[14], a, b), s1 = lut16(tb[15], a, b);
-                        w2g |= (((xb >> k) & 1u) ? s1 : s0) << (4 * k);
-                    }
-                    w21 = w2g;
-                }
-            }
-            xb ^= (xb >> 4) & 15u;                               // combine of the subtree root
-            // publish the 8 partial sums in the lane's own slot (read-modify-write keeps neighbouring ranges)
-            uint32_t *xo = X + ((8u * sidx) >> 5) * 32 + lane;
-            const int sh = (8 * sidx) & 31;
-            *xo = (*xo & ~(0xffu << sh)) | ((xb & 0xffu) << sh);
-            if (L > 1 && (sidx & 1) == 0) setown(pu, top);
-            __syncwarp();
-        };
-
-        auto iteration = [&](int s, const uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
-            load_bundle(nxt, (s + 1 == NS) ? 0 : s + 1);   // next subtree (wraps into the next pass)
+        for (int s = 0; s < NS; ++s) {
+            // ---- upper levels: g at the deepest ancestor whose right subtree starts here, then f down to depth top ----
             int dstart = 0;
             if (s != 0) {
                 const int t = __ffs(s) - 1;
                 const int dg = top - 1 - t;
-                fg_step(dg, (uint32_t)s >> (t + 1), std::true_type{});
+                fg_step(dg, (uint32_t)s >> (t + 1), true);
                 dstart = dg + 1;
             }
-            for (int dd = dstart; dd <= top - 1; ++dd) fg_step(dd, (uint32_t)s >> (top - dd), std::false_type{});
-            subtree8(s, cur);
+            for (int dd = dstart; dd <= top - 1; ++dd) fg_step(dd, (uint32_t)s >> (top - dd), false);
+
+            // ---- the 8-leaf subtree, state in registers, as a loop over its four leaf pairs ----
+            const uint32_t fz = (__ldg(fp.frozen_words + (s >> 2)) >> ((s & 3) * 8)) & 0xffu;
+            w3 = *level_ptr(top, vslot(top));
+            xb = 0;
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int pos = 2 * c4;
+                if ((c4 & 1) == 0) {
+                    uint32_t w2 = 0;
+                    if (c4 == 0) {          // A.f : 8 -> 4 symbols
+                        const uint32_t t = next_line();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) w2 |= lut16(t, nib(w3, k), nib(w3, k + 4)) << (4 * k);
+                    } else {                // A.g : u = the 4 partial sums of the left half
+                        const uint32_t t0 = next_line(), t1 = next_line();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t a = nib(w3, k), b = nib(w3, k + 4);
+                            const uint32_t s0 = lut16(t0, a, b), s1 = lut16(t1, a, b);
+                            w2 |= (((xb >> k) & 1u) ? s1 : s0) << (4 * k);
+                        }
+                    }
+                    const uint32_t t = next_line();   // B.f : 4 -> 2 symbols
+                    const uint32_t w1 = lut16(t, nib(w2, 0), nib(w2, 2)) | (lut16(t, nib(w2, 1), nib(w2, 3)) << 4);
+                    w21 = w2 | (w1 << 16);
+                } else {                    // B.g : u = the 2 partial sums of the left pair
+                    const uint32_t t0 = next_line(), t1 = next_line();
+                    const uint32_t c2 = w21 & 0xffffu;
+                    uint32_t w1 = 0;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t a = nib(c2, k), b = nib(c2, k + 2);
+                        const uint32_t s0 = lut16(t0, a, b), s1 = lut16(t1, a, b);
+                        w1 |= (((xb >> (pos - 2 + k)) & 1u) ? s1 : s0) << (4 * k);
+                    }
+                    w21 = c2 | (w1 << 16);
+                }
+#pragma unroll 1
+                for (int side = 0; side < 2; ++side) {
+                    // leaf symbol through the depth n-1 node: f table (left leaf) or g tables with u = left leaf's bit
+                    const uint32_t w1 = w21 >> 16;
+                    const uint32_t a = nib(w1, 0), b = nib(w1, 1);
+                    uint32_t sym;
+                    if (side == 0) {
+                        sym = lut16(next_line(), a, b);
+                    } else {
+                        const uint32_t t0 = next_line(), t1 = next_line();
+                        const uint32_t s0 = lut16(t0, a, b), s1 = lut16(t1, a, b);
+                        sym = ((xb >> pos) & 1u) ? s1 : s0;
+                    }
+                    const uint32_t lr = next_line();
+                    const int lp = pos + side;
+                    const bool frozen = (fz >> lp) & 1u;
+                    // leaf decision (PD/src/SCLUTDecoder.cpp:59-67 / SCLLUTDecoder.cpp:92-145)
+                    const int lo_ = __shfl_sync(kFull, (int)lr, 2 * sym), hi_ = __shfl_sync(kFull, (int)lr, 2 * sym + 1);
+                    const double DM = __hiloint2double(hi_, lo_);
+                    uint32_t bit = 0;
+                    if (L == 1) {
+                        bit = (!frozen && DM <= 0) ? 1u : 0u;
+                    } else if (frozen) {
+                        PM += fabs(DM) * (double)(DM < 0);
+                    } else {
+                        const uint32_t dec = (DM < 0) ? 1u : 0u;
+                        const double K0 = PM, K1 = PM + fabs(DM);
+                        __syncwarp();
+                        *reinterpret_cast<double2 *>(&KS[lane * 2]) = make_double2(K0, K1);
+                        // stable rank of (key, index) among the group's 2L keys == libstdc++ insertion sort for
+                        // 2L <= 16: a key sorts before mine if it is smaller, or equal with a lower index
+                        __syncwarp();
+                        int r0 = 0, r1 = 0;
+#pragma unroll
+                        for (int j = 0; j < L; ++j) {
+                            const double2 kf = *reinterpret_cast<const double2 *>(&KS[(gbase + j) * 2]);
+                            const bool jb = j < me;
+                            r0 += (jb ? !(K0 < kf.x) : (kf.x < K0)) + (kf.y < K0);
+                            r1 += !(K1 < kf.x) + (jb ? !(K1 < kf.y) : (kf.y < K1));
+                        }
+                        if (r0 < L) SEL[gbase + r0] = (uint32_t)me;
+                        if (r1 < L) SEL[gbase + r1] = (uint32_t)me | 16u;
+                        __syncwarp();
+                        const uint32_t sv = SEL[lane];
+                        const int p = gbase | (int)(sv & 15u);
+                        const uint32_t fl = sv >> 4;
+                        PM = KS[p * 2 + fl];
+                        bit = __shfl_sync(kFull, dec, p) ^ fl;
+                        w3 = __shfl_sync(kFull, w3, p);
+                        w21 = __shfl_sync(kFull, w21, p);
+                        xb = __shfl_sync(kFull, xb, p);
+                        pv = __shfl_sync(kFull, pv, p);
+                        pu = __shfl_sync(kFull, pu, p);
+                    }
+                    xb = (xb & ~(1u << lp)) | (bit << lp);
+                }
+                xb ^= ((xb >> (pos + 1)) & 1u) << pos;                     // combine of the depth n-1 node
+                if (c4 & 1) xb ^= ((xb >> pos) & 3u) << (pos - 2);         // combine of the depth n-2 node
+            }
+            xb ^= (xb >> 4) & 15u;                                         // combine of the subtree root
+            {   // publish the 8 partial sums in the lane's own slot (read-modify-write keeps neighbouring ranges)
+                uint32_t *xo = X + ((8u * s) >> 5) * 32 + lane;
+                const int sh = (8 * s) & 31;
+                *xo = (*xo & ~(0xffu << sh)) | ((xb & 0xffu) << sh);
+                if (L > 1 && (s & 1) == 0) setown(pu, top);
+                __syncwarp();
+            }
             const int t1n = __ffs(~s) - 1;   // trailing ones of s
             for (int k = 0; k < t1n; ++k) combine(top - 1 - k, (uint32_t)s >> (k + 1));
-        };
-        for (int s = 0; s < NS; s += 2) {
-            iteration(s, bufA, bufB);
-            iteration(s + 1, bufB, bufA);
         }
 
         // ---------------- epilogue: choose the path, u = x F^{(x)n}, gather the information bits ----------------
         const int NW = N >> 5;
-        uint32_t *SCR = IN;   // level-0 buffer is dead now: SCR[w*FPW + grp]
+        // scratch for u: SC[w*FPW + grp]; for L == 1 every lane transforms its own X column in place
+        uint32_t *SC = (L == 1) ? X : SCR;
         auto transform_from = [&](int src_lane) {
             __syncwarp();
             for (int w = me; w < NW; w += L) {
@@ -380,18 +370,18 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 x ^= (x >> 4) & 0x0f0f0f0fu;
                 x ^= (x >> 8) & 0x00ff00ffu;
                 x ^= (x >> 16) & 0x0000ffffu;
-                SCR[w * FPW + grp] = x;
+                SC[w * FPW + grp] = x;
             }
             __syncwarp();
             for (int m = 1; m < NW; m <<= 1) {
                 for (int t = me; t < NW / 2; t += L) {
                     const int w = ((t & ~(m - 1)) << 1) | (t & (m - 1));
-                    SCR[w * FPW + grp] ^= SCR[(w + m) * FPW + grp];
+                    SC[w * FPW + grp] ^= SC[(w + m) * FPW + grp];
                 }
                 __syncwarp();
             }
         };
-        auto ubit = [&](int pos) -> uint32_t { return (SCR[(pos >> 5) * FPW + grp] >> (pos & 31)) & 1u; };
+        auto ubit = [&](int pos) -> uint32_t { return (SC[(pos >> 5) * FPW + grp] >> (pos & 31)) & 1u; };
 
         int winner = lane;
         if (L > 1) {
@@ -520,63 +510,53 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
         memcpy(line, &llr[llr_off[r]], (size_t)len * sizeof(double));
         stream.insert(stream.end(), line, line + 32);
     };
-    // (a) upper levels (depths 0..n-4), in the order iteration() issues its f/g steps
+    // one stream, in the exact order the kernel consumes it: per 8-leaf subtree s
+    //   [g of the ancestor at depth top-1-ctz(s)] [f chain down to depth top-1]
+    //   A.f  B0.f | pair0: C.f llr C.g0 C.g1 llr | B0.g0 B0.g1 | pair1 | A.g0 A.g1 B1.f | pair2 | B1.g0 B1.g1 | pair3
     const int top = n - 3, NS = N >> 3;
+    auto heap = [&](int depth, int node) { return (1 << depth) + node - 1; };
     for (int sidx = 0; sidx < NS; ++sidx) {
         int dstart = 0;
         if (sidx != 0) {
             int t = __builtin_ctz((unsigned)sidx);
             int dg = top - 1 - t;
-            push_g((1 << dg) + (sidx >> (t + 1)) - 1);
+            push_g(heap(dg, sidx >> (t + 1)));
             dstart = dg + 1;
         }
-        for (int dd = dstart; dd <= top - 1; ++dd) push_f((1 << dd) + (sidx >> (top - dd)) - 1);
-    }
-    std::vector<uint32_t> upper;
-    upper.swap(stream);
-    // (b) one bundle of 29 (+3 pad) lines per 8-leaf subtree, in the order subtree8() indexes them:
-    //     0 A.f | per half m: 1+15m B.f, per pair c: +1+7c C.f, llr(left), C.g0, C.g1, llr(right); +6,+7 B.g0,B.g1 | 14,15 A.g0,A.g1
-    std::vector<uint32_t> bundles((size_t)NS * 32 * 32, 0);
-    for (int sidx = 0; sidx < NS; ++sidx) {
-        stream.clear();
-        auto heap = [&](int depth, int node) { return (1 << depth) + node - 1; };
+        for (int dd = dstart; dd <= top - 1; ++dd) push_f(heap(dd, sidx >> (top - dd)));
         const int A = heap(top, sidx);
-        std::vector<uint32_t> lines((size_t)32 * 32, 0);
-        auto put = [&](int line) {   // moves the most recently pushed line(s) of `stream` into `lines`
-            memcpy(&lines[(size_t)line * 32], &stream[stream.size() - 32], 32 * sizeof(uint32_t));
-        };
-        auto put2 = [&](int line) {
-            memcpy(&lines[(size_t)line * 32], &stream[stream.size() - 64], 64 * sizeof(uint32_t));
-        };
-        push_f(A); put(0);
-        push_g(A); put2(14);
-        for (int m = 0; m < 2; ++m) {
-            const int Bn = heap(top + 1, 2 * sidx + m), bl = 1 + 15 * m;
-            push_f(Bn); put(bl);
-            push_g(Bn); put2(bl + 6);
-            for (int c = 0; c < 2; ++c) {
-                const int Cn = heap(top + 2, 4 * sidx + 2 * m + c), cl = bl + 1 + 7 * c;
-                const int leaf0 = 8 * sidx + 4 * m + 2 * c;
-                push_f(Cn); put(cl);
-                push_llr(leaf0); put(cl + 1);
-                push_g(Cn); put2(cl + 2);
-                push_llr(leaf0 + 1); put(cl + 4);
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int Bn = heap(top + 1, 2 * sidx + (c4 >> 1));
+            if ((c4 & 1) == 0) {
+                if (c4 == 0) push_f(A); else push_g(A);
+                push_f(Bn);
+            } else {
+                push_g(Bn);
             }
+            const int Cn = heap(top + 2, 4 * sidx + c4), leaf0 = 8 * sidx + 2 * c4;
+            push_f(Cn);
+            push_llr(leaf0);
+            push_g(Cn);
+            push_llr(leaf0 + 1);
         }
-        // lane-transposed: chunk j (lines 4j..4j+3), lane l -> 4 consecutive words
-        uint32_t *dst = &bundles[(size_t)sidx * 1024];
-        for (int j = 0; j < 8; ++j)
-            for (int l = 0; l < 32; ++l)
-                for (int q = 0; q < 4; ++q) dst[(j * 32 + l) * 4 + q] = lines[(size_t)(4 * j + q) * 32 + l];
     }
-    stream.swap(upper);
+    // pad to whole chunks of 4 lines and transpose each chunk to [lane][4]
+    while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
+    const int n_lines = (int)(stream.size() / 32);
+    {
+        std::vector<uint32_t> tr(stream.size());
+        for (int c = 0; c < n_lines / 4; ++c)
+            for (int l = 0; l < 32; ++l)
+                for (int q = 0; q < 4; ++q) tr[((size_t)c * 32 + l) * 4 + q] = stream[((size_t)c * 4 + q) * 32 + l];
+        stream.swap(tr);
+    }
     FastParams &P = pl->p;
     P = FastParams{};
-    P.n_lines = (int)(stream.size() / 32);
-    if (P.n_lines < 1) return;
+    P.n_chunks = n_lines / 4;
+    if (P.n_chunks < 1) return;
     std::vector<uint32_t> fw((N + 31) / 32, 0);
     for (int i = 0; i < N; ++i) if (frozen[i] == 1) fw[i >> 5] |= 1u << (i & 31);
-    if (!fast_upload(pl, stream, &P.stream) || !fast_upload(pl, bundles, &P.bundles) || !fast_upload(pl, fw, &P.frozen_words)) { free_fast_plan(pl); return; }
+    if (!fast_upload(pl, stream, &P.stream) || !fast_upload(pl, fw, &P.frozen_words)) { free_fast_plan(pl); return; }
     if (d.ca) {
         // remainder of the unit message e_k under the reference's long division (utils.cpp:77-93): linear, so the
         // CRC of a word is the XOR of the remainders of its set bits
@@ -596,18 +576,24 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
         for (int k = 0; k < d.crc_check; ++k) cm |= 1u << (d.crc_n - 1 - k);
         P.crc_checkmask = cm;
     }
-    // level offsets (words) of the nibble-packed value levels 1..n-1
-    int off = 0;
-    for (int lev = 1; lev <= n - 3; ++lev) {
-        P.voff[lev] = off;
-        off += std::max(1, (N >> lev) / 8);
-    }
-    P.vwords = off;
-    P.xwords = N / 32;
-    P.inwords = N / 8;
+    // value levels 1..top (nibble-packed, (N>>lev)/8 words each): the big ones (> 8 words per lane) go to the
+    // global workspace -- they are touched only a handful of times per frame and stay L2-resident --, the small,
+    // hot ones stay in shared memory.  This is what sets the occupancy (warps per SM).
     const int FPW = 32 / L;
-    size_t words = (size_t)P.vwords * 32 + (size_t)P.xwords * 32 + (size_t)P.inwords * FPW + kRing * 32 + 128 + 32;
+    int gl = 0, goff = 0, soff = 0;
+    for (int lev = 1; lev <= n - 3; ++lev) {
+        int words = (N >> lev) / 8;
+        if (words > 8) { P.voff[lev] = goff; goff += words; gl = lev; }
+        else { P.voff[lev] = soff; soff += words; }
+    }
+    P.gl = gl;
+    P.gwords = std::max(goff, 1);
+    P.vwords = std::max(soff, 1);
+    P.xwords = N / 32;
+    P.scrwords = (L == 1) ? 0 : (N / 32) * FPW;
+    size_t words = (size_t)P.vwords * 32 + (size_t)P.xwords * 32 + (size_t)P.scrwords + kRingChunks * 128 + 128 + 32;
     pl->smem = words * 4;
+    pl->ws_bytes_per_cta = (size_t)P.gwords * 32 * 4;
     pl->logL = logL;
     pl->ca = d.ca != 0;
     const void *fn = fast_kernel_fn(logL, pl->ca);
@@ -620,12 +606,16 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
     pl->ok = true;
 }
 
-inline int launch_fast_lut(const Dev &d, const FastPlan &pl, const void *d_in, int dtype, long long B, uint8_t *d_out,
-                           cudaStream_t s, int *d_err, double *dbg_pm, int *dbg_win, int sm_count) {
+inline int fast_grid(const FastPlan &pl, long long B, int sm_count) {
     const int L = 1 << pl.logL, FPW = 32 / L;
     long long groups = (B + FPW - 1) / FPW;
-    int grid = (int)std::min<long long>(groups, (long long)sm_count * pl.ctas_per_sm);
-#define PB_LAUNCH(LOGL, CAF) scl_lut_warp_kernel<LOGL, CAF><<<grid, 32, pl.smem, s>>>(d, pl.p, d_in, dtype, d_out, B, d_err, dbg_pm, dbg_win)
+    return (int)std::max<long long>(1, std::min<long long>(groups, (long long)sm_count * pl.ctas_per_sm));
+}
+
+inline int launch_fast_lut(const Dev &d, const FastPlan &pl, const void *d_in, int dtype, long long B, uint8_t *d_out,
+                           cudaStream_t s, uint32_t *ws, int *d_err, double *dbg_pm, int *dbg_win, int sm_count) {
+    const int grid = fast_grid(pl, B, sm_count);
+#define PB_LAUNCH(LOGL, CAF) scl_lut_warp_kernel<LOGL, CAF><<<grid, 32, pl.smem, s>>>(d, pl.p, d_in, dtype, d_out, B, ws, d_err, dbg_pm, dbg_win)
     switch (pl.logL) {
     case 0: PB_LAUNCH(0, false); break;
     case 1: if (pl.ca) PB_LAUNCH(1, true); else PB_LAUNCH(1, false); break;
