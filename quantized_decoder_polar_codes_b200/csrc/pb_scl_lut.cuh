@@ -98,21 +98,28 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     //      host lays the lines out in consumption order, 4 lines per lane-transposed 512-byte chunk, and each
     //      lane streams ITS 16 bytes of every chunk with cp.async into a private ring (no cross-lane sync). ----
     int fetch_chunk = 0;    // stream position of the next chunk to prefetch
-    unsigned line_no = 0;   // lines consumed so far
+    unsigned chunk_no = 0;  // chunks consumed so far
     const uint4 *stream4 = reinterpret_cast<const uint4 *>(fp.stream) + lane;
-    auto issue_chunk = [&](int slot) {
+    auto issue_chunk = [&](unsigned slot) {
         cp_async16(&RING[slot * 128 + lane * 4], stream4 + (size_t)fetch_chunk * 32);
         fetch_chunk = (fetch_chunk + 1 == fp.n_chunks) ? 0 : fetch_chunk + 1;
     };
     for (int i = 0; i < kRingChunks - 1; ++i) issue_chunk(i);
+    auto next_chunk = [&]() -> uint4 {
+        const unsigned slot = chunk_no & (kRingChunks - 1);
+        issue_chunk((slot + kRingChunks - 1) & (kRingChunks - 1));   // refill the slot consumed before this one
+        cp_async_wait<kRingChunks - 1>();                            // ... and make sure this chunk has landed
+        ++chunk_no;
+        return *reinterpret_cast<const uint4 *>(&RING[slot * 128 + lane * 4]);
+    };
+    // upper-level steps take their 1 or 2 lines one at a time out of the current chunk
+    uint4 ucur = make_uint4(0, 0, 0, 0);
+    int uq = 4;
     auto next_line = [&]() -> uint32_t {
-        const unsigned q = line_no & 3u, slot = (line_no >> 2) & (kRingChunks - 1);
-        if (q == 0) {
-            issue_chunk((slot + kRingChunks - 1) & (kRingChunks - 1));   // refill the chunk consumed before this one
-            cp_async_wait<kRingChunks - 1>();                            // ... and make sure this one has landed
-        }
-        ++line_no;
-        return RING[slot * 128 + lane * 4 + q];
+        if (uq == 4) { ucur = next_chunk(); uq = 0; }
+        const uint32_t v = uq == 0 ? ucur.x : uq == 1 ? ucur.y : uq == 2 ? ucur.z : ucur.w;
+        ++uq;
+        return v;
     };
     auto lut16 = [&](uint32_t treg, uint32_t a, uint32_t b) -> uint32_t {
         const uint32_t w = __shfl_sync(kFull, treg, a * 2 + (b >> 3));
@@ -249,39 +256,40 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             }
             for (int dd = dstart; dd <= top - 1; ++dd) fg_step(dd, (uint32_t)s >> (top - dd), false);
 
-            // ---- the 8-leaf subtree, state in registers, as a loop over its four leaf pairs ----
+            // ---- the 8-leaf subtree, state in registers, as a loop over its four leaf pairs.  Each pair consumes
+            //      exactly two chunks of the stream: [P0 P1 P2 C.f] [llr C.g0 C.g1 llr] with (P0,P1,P2) =
+            //      (A.f,-,B.f) | (B.g0,B.g1,-) | (A.g0,A.g1,B.f) | (B.g0,B.g1,-) ----
+            uq = 4;   // the upper part is padded to a chunk boundary
             const uint32_t fz = (__ldg(fp.frozen_words + (s >> 2)) >> ((s & 3) * 8)) & 0xffu;
             w3 = *level_ptr(top, vslot(top));
             xb = 0;
 #pragma unroll 1
             for (int c4 = 0; c4 < 4; ++c4) {
                 const int pos = 2 * c4;
+                const uint4 c0 = next_chunk(), c1 = next_chunk();
                 if ((c4 & 1) == 0) {
                     uint32_t w2 = 0;
                     if (c4 == 0) {          // A.f : 8 -> 4 symbols
-                        const uint32_t t = next_line();
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) w2 |= lut16(t, nib(w3, k), nib(w3, k + 4)) << (4 * k);
+                        for (int k = 0; k < 4; ++k) w2 |= lut16(c0.x, nib(w3, k), nib(w3, k + 4)) << (4 * k);
                     } else {                // A.g : u = the 4 partial sums of the left half
-                        const uint32_t t0 = next_line(), t1 = next_line();
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t a = nib(w3, k), b = nib(w3, k + 4);
-                            const uint32_t s0 = lut16(t0, a, b), s1 = lut16(t1, a, b);
+                            const uint32_t s0 = lut16(c0.x, a, b), s1 = lut16(c0.y, a, b);
                             w2 |= (((xb >> k) & 1u) ? s1 : s0) << (4 * k);
                         }
                     }
-                    const uint32_t t = next_line();   // B.f : 4 -> 2 symbols
-                    const uint32_t w1 = lut16(t, nib(w2, 0), nib(w2, 2)) | (lut16(t, nib(w2, 1), nib(w2, 3)) << 4);
+                    // B.f : 4 -> 2 symbols
+                    const uint32_t w1 = lut16(c0.z, nib(w2, 0), nib(w2, 2)) | (lut16(c0.z, nib(w2, 1), nib(w2, 3)) << 4);
                     w21 = w2 | (w1 << 16);
                 } else {                    // B.g : u = the 2 partial sums of the left pair
-                    const uint32_t t0 = next_line(), t1 = next_line();
                     const uint32_t c2 = w21 & 0xffffu;
                     uint32_t w1 = 0;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const uint32_t a = nib(c2, k), b = nib(c2, k + 2);
-                        const uint32_t s0 = lut16(t0, a, b), s1 = lut16(t1, a, b);
+                        const uint32_t s0 = lut16(c0.x, a, b), s1 = lut16(c0.y, a, b);
                         w1 |= (((xb >> (pos - 2 + k)) & 1u) ? s1 : s0) << (4 * k);
                     }
                     w21 = c2 | (w1 << 16);
@@ -293,13 +301,12 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                     const uint32_t a = nib(w1, 0), b = nib(w1, 1);
                     uint32_t sym;
                     if (side == 0) {
-                        sym = lut16(next_line(), a, b);
+                        sym = lut16(c0.w, a, b);
                     } else {
-                        const uint32_t t0 = next_line(), t1 = next_line();
-                        const uint32_t s0 = lut16(t0, a, b), s1 = lut16(t1, a, b);
+                        const uint32_t s0 = lut16(c1.y, a, b), s1 = lut16(c1.z, a, b);
                         sym = ((xb >> pos) & 1u) ? s1 : s0;
                     }
-                    const uint32_t lr = next_line();
+                    const uint32_t lr = side == 0 ? c1.x : c1.w;
                     const int lp = pos + side;
                     const bool frozen = (fz >> lp) & 1u;
                     // leaf decision (PD/src/SCLUTDecoder.cpp:59-67 / SCLLUTDecoder.cpp:92-145)
@@ -511,10 +518,12 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
         stream.insert(stream.end(), line, line + 32);
     };
     // one stream, in the exact order the kernel consumes it: per 8-leaf subtree s
-    //   [g of the ancestor at depth top-1-ctz(s)] [f chain down to depth top-1]
-    //   A.f  B0.f | pair0: C.f llr C.g0 C.g1 llr | B0.g0 B0.g1 | pair1 | A.g0 A.g1 B1.f | pair2 | B1.g0 B1.g1 | pair3
+    //   [g of the ancestor at depth top-1-ctz(s)] [f chain down to depth top-1]      padded to a 4-line chunk
+    //   then per leaf pair c4 two chunks: [P0 P1 P2 C.f] [llr(left) C.g0 C.g1 llr(right)] with
+    //   (P0,P1,P2) = (A.f,-,B.f) for c4=0, (A.g0,A.g1,B.f) for c4=2, (B.g0,B.g1,-) for c4 odd
     const int top = n - 3, NS = N >> 3;
     auto heap = [&](int depth, int node) { return (1 << depth) + node - 1; };
+    auto push_pad = [&]() { stream.insert(stream.end(), 32, 0u); };
     for (int sidx = 0; sidx < NS; ++sidx) {
         int dstart = 0;
         if (sidx != 0) {
@@ -524,15 +533,13 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
             dstart = dg + 1;
         }
         for (int dd = dstart; dd <= top - 1; ++dd) push_f(heap(dd, sidx >> (top - dd)));
+        while ((stream.size() / 32) % 4) push_pad();
         const int A = heap(top, sidx);
         for (int c4 = 0; c4 < 4; ++c4) {
             const int Bn = heap(top + 1, 2 * sidx + (c4 >> 1));
-            if ((c4 & 1) == 0) {
-                if (c4 == 0) push_f(A); else push_g(A);
-                push_f(Bn);
-            } else {
-                push_g(Bn);
-            }
+            if (c4 == 0) { push_f(A); push_pad(); push_f(Bn); }
+            else if (c4 == 2) { push_g(A); push_f(Bn); }
+            else { push_g(Bn); push_pad(); }
             const int Cn = heap(top + 2, 4 * sidx + c4), leaf0 = 8 * sidx + 2 * c4;
             push_f(Cn);
             push_llr(leaf0);
