@@ -28,8 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N, K, L, Q = 1024, 512, 8, 16
-EBN0_DB = 2.0
-WORKLOAD = "SCL-LUT N=1024 A=K=512 L=8 QDecoder=QChannel=16 (uniform-grid min-sum LUTs), AWGN Eb/N0=2.0 dB, NR-sequence frozen set"
+EBN0_DB = 3.0
+WORKLOAD = "SCL-LUT N=1024 A=K=512 L=8 QDecoder=QChannel=16 (uniform-grid min-sum LUTs), AWGN Eb/N0=3.0 dB, NR-sequence frozen set"
 METRIC = "decoded frames/s (info Gbit/s = frames/s*512/1e9), N=1024 L=8 SCL-LUT"
 BYTES_PER_FRAME = N + K  # uint8 symbols in + uint8 bits out
 
@@ -161,7 +161,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8 symbols + f64 path metrics", "data": "synthetic",
+        "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step": cores * fpc, "info_gbit_s": fps * K / 1e9},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
                          "sample": f"{fpc} frames per core per step, one pinned process per core, per-frame decode() calls"},
@@ -176,11 +176,11 @@ def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     import quantized_decoder_polar_codes_b200 as q
     from quantized_decoder_polar_codes_b200 import capi
+    from quantized_decoder_polar_codes_b200 import distributed as D
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    D.init("nccl", dev)
     F = args.batch
     kw, sym0, msg0 = make_workload(min(F, 8192), seed=rank)
     sym, msg = tile_frames(sym0, msg0, F)
@@ -197,12 +197,10 @@ def run_ours(args, rank, local_rank, world):
     def step_device():
         capi.decode_device(dec, d_in.data_ptr(), capi.PD_U8, F, d_out.data_ptr(), stream)
         capi.check(lib.pd_count_errors(d_out.data_ptr(), d_truth.data_ptr(), F, K, counters.data_ptr(), stream))
-        if world > 1:
-            dist.all_reduce(counters)   # the path's only exchange: 2 x int64 over NCCL/NVLink
+        D.allreduce_counters(counters)   # the path's only exchange: 2 x int64 over NCCL/NVLink
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         torch.cuda.synchronize()
 
     launches0 = lib.pd_launch_count()
@@ -223,18 +221,15 @@ def run_ours(args, rank, local_rank, world):
             capi.decode_device(dec, d_in.data_ptr(), capi.PD_U8, F, d_out.data_ptr(), stream)
             kev[i][1].record()
             capi.check(lib.pd_count_errors(d_out.data_ptr(), d_truth.data_ptr(), F, K, counters.data_ptr(), stream))
-            if world > 1:
-                dist.all_reduce(counters)
+            D.allreduce_counters(counters)
         ev[1].record()
         barrier()
         l_after = lib.pd_launch_count()
     capi.sync_check(dec, stream)
     elapsed_ms = ev[0].elapsed_time(ev[1])
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = D.max_over_ranks(elapsed_ms, dev)
+    kernel_ms = D.max_over_ranks(kernel_ms, dev)
     value = world * F * args.steps / (elapsed_ms / 1e3)
     cnt = counters.cpu().tolist()
     total_frames = world * F * args.steps if world > 1 else F * args.steps
@@ -253,10 +248,7 @@ def run_ours(args, rank, local_rank, world):
         capi.decode_host(dec, h_in_p, capi.PD_U8, F, h_out_p)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * F * args.steps / float(t.item())
+    e2e_value = world * F * args.steps / D.max_over_ranks(e2e_s, dev)
     same = bool((h_out == d_out.cpu().numpy()).all())
     lib.pd_host_free(h_in_p)
     lib.pd_host_free(h_out_p)
@@ -269,18 +261,25 @@ def run_ours(args, rank, local_rank, world):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = BYTES_PER_FRAME * F / (kernel_ms / 1e3) / 1e9
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel, per frame
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("kernel") == dec.kernel:
+                traffic = tj["dram_bytes_per_frame"] * F
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8 symbols + f64 path metrics", "data": "synthetic",
+            "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "info_gbit_s": value * K / 1e9, "kernel": dec.kernel,
                        "l2": "inputs+outputs per step exceed L2 (no flush needed)" if F * BYTES_PER_FRAME > 126 * 2 ** 20 else "batch below L2 size",
                        "bit_errors": cnt[0], "block_errors": cnt[1], "frames_counted": total_frames,
                        "e2e_equals_device_output": same},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "kernel_ms": kernel_ms, "bytes_per_frame": BYTES_PER_FRAME,
-                         "note": "HBM-nominal codec path; really bound by the serial LUT/list-management chain per frame (see DESIGN.md)"},
+                         "note": "HBM-nominal codec path; the kernel is SM-issue bound, not HBM bound (see DESIGN.md 4.1, profiles/)"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * N, "d2h_bytes_per_step": F * K},
             "gpu_launches": int(l_after - l_before),
             "clocks": clk.summary(),
@@ -301,7 +300,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=131072, help="frames per step per GPU")
