@@ -17,8 +17,8 @@
 #include <vector>
 
 #include "../../include/polar_b200.h"
-#include "pb_generic.cuh"
 #include "pb_internal.h"
+#include "pb_generic.cuh"
 #include "pb_scl_lut.cuh"
 
 using namespace pb;
@@ -228,7 +228,11 @@ int build_lut(pd_decoder *D, const pd_config *c) {
     if ((rc = upload(D, tabs, &D->dev.tabs))) return rc;
     if ((rc = upload(D, llr, &D->dev.llr))) return rc;
     if ((rc = upload(D, loff, &D->dev.llr_off))) return rc;
-    plan_fast_lut(D->dev, PD_SCLUT, PD_SCLLUT, PD_CASCLLUT, tabs, pool, llr, loff, c->llr_off, c->frozen_bits, D->dev.crc_taps, &D->fast);
+    {
+        const bool fastk = is_fast(kind);
+        const int max_special = !fastk ? -1 : (is_list(kind) ? 2 : 3);
+        plan_fast_lut(D->dev, true, c->node_type, max_special, tabs, pool, llr, loff, c->llr_off, c->frozen_bits, D->dev.crc_taps, &D->fast);
+    }
     return PD_OK;
 }
 

@@ -23,9 +23,11 @@
 
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <type_traits>
 #include <vector>
 
+#include "pb_generic.cuh"
 #include "pb_internal.h"
 
 namespace pb {
@@ -33,10 +35,20 @@ namespace pb {
 constexpr int kRingChunks = 4;     // ring slots per lane, 4 lines (16 bytes per lane) each; 3 chunks in flight
 constexpr unsigned kFull = 0xffffffffu;
 
+enum FastOp : uint32_t {
+    FOP_UF = 0, FOP_UG, FOP_UC,          // f / g / combine at depth <= top-1 (levels in memory)
+    FOP_SUB8,                            // a plain 8-leaf subtree (registers)
+    FOP_SBEGIN, FOP_SF3, FOP_SG3, FOP_SF2, FOP_SG2, FOP_SPAIR, FOP_SC2, FOP_SC3, FOP_SEND,   // a subtree with special nodes inside
+    FOP_SP                               // Fast-SSC special node: arg = 0 R0, 1 R1, 2 REP, 3 SPC
+};
+
 struct FastParams {
     const uint32_t *stream;        // table stream in consumption order: [chunk][lane][4 lines' word of that lane]
     int n_chunks;
     const uint32_t *frozen_words;  // frozen mask, 32 leaves per word
+    const uint2 *ops;              // compiled tree walk: x = type | depth<<8 | arg<<16, y = node
+    int n_ops;
+    int r1_words;                  // shared-memory words for the R1 scratch (0 when the code has no R1 node)
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
     int vwords, xwords, scrwords;  // shared-memory words per lane: value levels gl+1..top, X; scratch words per warp
@@ -50,6 +62,7 @@ struct FastPlan {
     const char *name = "generic";
     int logL = 0;
     bool ca = false;
+    bool fastk = false;   // the walk contains Fast-SSC special nodes
     FastParams p{};
     size_t smem = 0;
     size_t ws_bytes_per_cta = 0;
@@ -72,7 +85,7 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x) {
     return (x & 0xfu) | ((x >> 4) & 0xf0u) | ((x >> 8) & 0xf00u) | ((x >> 12) & 0xf000u);
 }
 
-template <int LOGL, bool CA>
+template <int LOGL, bool CA, bool FAST>
 __global__ void __launch_bounds__(32)
 scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastParams fp, const void *__restrict__ in, int in_dtype,
                     uint8_t *__restrict__ out, long long B, uint32_t *__restrict__ ws, int *err_flag, double *dbg_pm, int *dbg_win) {
@@ -82,7 +95,6 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     const int lane = threadIdx.x;
     const int grp = lane >> LOGL, me = lane & (L - 1), gbase = lane & ~(L - 1);
     const int N = d.N, n = d.n;
-    const int NS = N >> 3;          // number of 8-leaf subtrees
     const int top = n - 3;          // depth of the subtree roots = deepest value level kept in memory
 
     uint32_t *V = sm;                                  // value levels gl+1..top, [word][lane]
@@ -92,6 +104,8 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     uint32_t *G = ws + (size_t)blockIdx.x * fp.gwords * 32;   // value levels 1..gl, [word][lane], L2-resident
     double *KS = reinterpret_cast<double *>(RING + kRingChunks * 128);   // [32][2]
     uint32_t *SEL = reinterpret_cast<uint32_t *>(KS + 64);               // [32]
+    double *R1S = reinterpret_cast<double *>(SEL + 32);                  // [7][32] smallest |llr| of an R1 node (Fast kinds)
+    uint32_t *R1Q = reinterpret_cast<uint32_t *>(R1S + 7 * 32);          // [7][32] their positions
 
     // ---- table stream.  Every f/g table (one 128-byte line = 16x16 nibbles) and every leaf LLR row (16 doubles)
     //      is consumed exactly once per pass, in a fixed order, and lane l only ever needs word l of a line.  The
@@ -245,123 +259,319 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         uint32_t w21 = 0;    // [15:0] 4 symbols of the depth top+1 node, [23:16] 2 symbols of the depth top+2 node
         uint32_t xb = 0;     // partial sums of the subtree, in place (bit i = leaf i)
 
-        for (int s = 0; s < NS; ++s) {
-            // ---- upper levels: g at the deepest ancestor whose right subtree starts here, then f down to depth top ----
-            int dstart = 0;
-            if (s != 0) {
-                const int t = __ffs(s) - 1;
-                const int dg = top - 1 - t;
-                fg_step(dg, (uint32_t)s >> (t + 1), true);
-                dstart = dg + 1;
+        // mink + list permutation (PD/src/SCLLUTDecoder.cpp:8-22,106-145): every path offers the keys K0 (index
+        // me, "keep") and K1 (index L+me, "flip"); the L smallest of the group's 2L keys in std::sort order survive.
+        // For 2L <= 16 libstdc++ is an insertion sort, i.e. a stable rank of (key, index).  Returns the lane of the
+        // parent path and the flip flag; PM, the pointer words and the subtree registers follow the parent.
+        auto fork = [&](double K0, double K1, int &p, uint32_t &fl) {
+            __syncwarp();
+            *reinterpret_cast<double2 *>(&KS[lane * 2]) = make_double2(K0, K1);
+            __syncwarp();
+            int r0 = 0, r1 = 0;
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                const double2 kf = *reinterpret_cast<const double2 *>(&KS[(gbase + j) * 2]);
+                const bool jb = j < me;
+                r0 += (jb ? !(K0 < kf.x) : (kf.x < K0)) + (kf.y < K0);
+                r1 += !(K1 < kf.x) + (jb ? !(K1 < kf.y) : (kf.y < K1));
             }
-            for (int dd = dstart; dd <= top - 1; ++dd) fg_step(dd, (uint32_t)s >> (top - dd), false);
-
-            // ---- the 8-leaf subtree, state in registers, as a loop over its four leaf pairs.  Each pair consumes
-            //      exactly two chunks of the stream: [P0 P1 P2 C.f] [llr C.g0 C.g1 llr] with (P0,P1,P2) =
-            //      (A.f,-,B.f) | (B.g0,B.g1,-) | (A.g0,A.g1,B.f) | (B.g0,B.g1,-) ----
-            uq = 4;   // the upper part is padded to a chunk boundary
-            const uint32_t fz = (__ldg(fp.frozen_words + (s >> 2)) >> ((s & 3) * 8)) & 0xffu;
-            w3 = *level_ptr(top, vslot(top));
-            xb = 0;
-#pragma unroll 1
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const int pos = 2 * c4;
-                const uint4 c0 = next_chunk(), c1 = next_chunk();
-                if ((c4 & 1) == 0) {
-                    uint32_t w2 = 0;
-                    if (c4 == 0) {          // A.f : 8 -> 4 symbols
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) w2 |= lut16(c0.x, nib(w3, k), nib(w3, k + 4)) << (4 * k);
-                    } else {                // A.g : u = the 4 partial sums of the left half
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t a = nib(w3, k), b = nib(w3, k + 4);
-                            const uint32_t s0 = lut16(c0.x, a, b), s1 = lut16(c0.y, a, b);
-                            w2 |= (((xb >> k) & 1u) ? s1 : s0) << (4 * k);
-                        }
-                    }
-                    // B.f : 4 -> 2 symbols
-                    const uint32_t w1 = lut16(c0.z, nib(w2, 0), nib(w2, 2)) | (lut16(c0.z, nib(w2, 1), nib(w2, 3)) << 4);
-                    w21 = w2 | (w1 << 16);
-                } else {                    // B.g : u = the 2 partial sums of the left pair
-                    const uint32_t c2 = w21 & 0xffffu;
-                    uint32_t w1 = 0;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint32_t a = nib(c2, k), b = nib(c2, k + 2);
-                        const uint32_t s0 = lut16(c0.x, a, b), s1 = lut16(c0.y, a, b);
-                        w1 |= (((xb >> (pos - 2 + k)) & 1u) ? s1 : s0) << (4 * k);
-                    }
-                    w21 = c2 | (w1 << 16);
+            if (r0 < L) SEL[gbase + r0] = (uint32_t)me;
+            if (r1 < L) SEL[gbase + r1] = (uint32_t)me | 16u;
+            __syncwarp();
+            const uint32_t sv = SEL[lane];
+            p = gbase | (int)(sv & 15u);
+            fl = sv >> 4;
+            PM = KS[p * 2 + fl];
+            w3 = __shfl_sync(kFull, w3, p);
+            w21 = __shfl_sync(kFull, w21, p);
+            xb = __shfl_sync(kFull, xb, p);
+            pv = __shfl_sync(kFull, pv, p);
+            pu = __shfl_sync(kFull, pu, p);
+        };
+        auto llr_of = [&](uint32_t lr, uint32_t sym) -> double {
+            const int lo_ = __shfl_sync(kFull, (int)lr, 2 * sym), hi_ = __shfl_sync(kFull, (int)lr, 2 * sym + 1);
+            return __hiloint2double(hi_, lo_);
+        };
+        // result bits of a node at (dd,node) with `temp` <= 32 leaves -> in place (subtree register or own X slot)
+        auto put_bits = [&](int dd, uint32_t node, int temp, uint32_t bits) {
+            const uint32_t base = node * (uint32_t)temp;
+            if (dd > top) {
+                const int pos = (int)(base & 7u);
+                const uint32_t mask = ((1u << temp) - 1u) << pos;
+                xb = (xb & ~mask) | ((bits << pos) & mask);
+            } else {
+                uint32_t *xo = X + (base >> 5) * 32 + lane;
+                if (temp == 32) {
+                    *xo = bits;
+                } else {
+                    const int sh = (int)(base & 31u);
+                    const uint32_t mask = ((1u << temp) - 1u) << sh;
+                    *xo = (*xo & ~mask) | ((bits << sh) & mask);
                 }
-#pragma unroll 1
-                for (int side = 0; side < 2; ++side) {
-                    // leaf symbol through the depth n-1 node: f table (left leaf) or g tables with u = left leaf's bit
-                    const uint32_t w1 = w21 >> 16;
-                    const uint32_t a = nib(w1, 0), b = nib(w1, 1);
-                    uint32_t sym;
-                    if (side == 0) {
-                        sym = lut16(c0.w, a, b);
-                    } else {
-                        const uint32_t s0 = lut16(c1.y, a, b), s1 = lut16(c1.z, a, b);
-                        sym = ((xb >> pos) & 1u) ? s1 : s0;
-                    }
-                    const uint32_t lr = side == 0 ? c1.x : c1.w;
-                    const int lp = pos + side;
-                    const bool frozen = (fz >> lp) & 1u;
-                    // leaf decision (PD/src/SCLUTDecoder.cpp:59-67 / SCLLUTDecoder.cpp:92-145)
-                    const int lo_ = __shfl_sync(kFull, (int)lr, 2 * sym), hi_ = __shfl_sync(kFull, (int)lr, 2 * sym + 1);
-                    const double DM = __hiloint2double(hi_, lo_);
-                    uint32_t bit = 0;
-                    if (L == 1) {
-                        bit = (!frozen && DM <= 0) ? 1u : 0u;
-                    } else if (frozen) {
-                        PM += fabs(DM) * (double)(DM < 0);
-                    } else {
-                        const uint32_t dec = (DM < 0) ? 1u : 0u;
-                        const double K0 = PM, K1 = PM + fabs(DM);
-                        __syncwarp();
-                        *reinterpret_cast<double2 *>(&KS[lane * 2]) = make_double2(K0, K1);
-                        // stable rank of (key, index) among the group's 2L keys == libstdc++ insertion sort for
-                        // 2L <= 16: a key sorts before mine if it is smaller, or equal with a lower index
-                        __syncwarp();
-                        int r0 = 0, r1 = 0;
-#pragma unroll
-                        for (int j = 0; j < L; ++j) {
-                            const double2 kf = *reinterpret_cast<const double2 *>(&KS[(gbase + j) * 2]);
-                            const bool jb = j < me;
-                            r0 += (jb ? !(K0 < kf.x) : (kf.x < K0)) + (kf.y < K0);
-                            r1 += !(K1 < kf.x) + (jb ? !(K1 < kf.y) : (kf.y < K1));
-                        }
-                        if (r0 < L) SEL[gbase + r0] = (uint32_t)me;
-                        if (r1 < L) SEL[gbase + r1] = (uint32_t)me | 16u;
-                        __syncwarp();
-                        const uint32_t sv = SEL[lane];
-                        const int p = gbase | (int)(sv & 15u);
-                        const uint32_t fl = sv >> 4;
-                        PM = KS[p * 2 + fl];
-                        bit = __shfl_sync(kFull, dec, p) ^ fl;
-                        w3 = __shfl_sync(kFull, w3, p);
-                        w21 = __shfl_sync(kFull, w21, p);
-                        xb = __shfl_sync(kFull, xb, p);
-                        pv = __shfl_sync(kFull, pv, p);
-                        pu = __shfl_sync(kFull, pu, p);
-                    }
-                    xb = (xb & ~(1u << lp)) | (bit << lp);
-                }
-                xb ^= ((xb >> (pos + 1)) & 1u) << pos;                     // combine of the depth n-1 node
-                if (c4 & 1) xb ^= ((xb >> pos) & 3u) << (pos - 2);         // combine of the depth n-2 node
-            }
-            xb ^= (xb >> 4) & 15u;                                         // combine of the subtree root
-            {   // publish the 8 partial sums in the lane's own slot (read-modify-write keeps neighbouring ranges)
-                uint32_t *xo = X + ((8u * s) >> 5) * 32 + lane;
-                const int sh = (8 * s) & 31;
-                *xo = (*xo & ~(0xffu << sh)) | ((xb & 0xffu) << sh);
-                if (L > 1 && (s & 1) == 0) setown(pu, top);
+                if (L > 1 && (node & 1u) == 0) setown(pu, dd);
                 __syncwarp();
             }
-            const int t1n = __ffs(~s) - 1;   // trailing ones of s
-            for (int k = 0; k < t1n; ++k) combine(top - 1 - k, (uint32_t)s >> (k + 1));
+        };
+        // symbols of the special node at depth dd: word w (8 symbols) of its region
+        auto node_word = [&](int dd, int w) -> uint32_t {
+            if (dd == top + 2) return w21 >> 16;
+            if (dd == top + 1) return w21 & 0xffffu;
+            return level_ptr(dd, vslot(dd))[w * 32];
+        };
+
+        // Fast-SSC special node (R0 / R1 / REP, plus SPC for the non-list decoder): the LLR of element j is
+        // virtual_channel_llrs[dd-1][pos][symbol] (PD/src/FastSCLLUTDecoder.cpp:89,112,179), one stream line per element
+        auto special = [&](int spt, int dd, uint32_t node) {
+            const int temp = N >> dd;
+            const uint32_t full = temp >= 32 ? 0xffffffffu : ((1u << temp) - 1u);
+            if (L == 1) {
+                // PD/src/FastSCLUT.cpp:43-106
+                if (spt == 0) {                                   // R0
+                    if (temp <= 32) put_bits(dd, node, temp, 0u);
+                    else for (int w = 0; w < (temp >> 5); ++w) X[((node * (uint32_t)temp >> 5) + w) * 32 + lane] = 0u;
+                    return;
+                }
+                double S = 0, best = 0;
+                int parity = 0, amin = 0;
+                uint32_t bits = 0, sw = 0;
+                for (int j = 0; j < temp; ++j) {
+                    if ((j & 7) == 0) sw = node_word(dd, j >> 3);
+                    const double DM = llr_of(next_line(), nib(sw, j & 7));
+                    const uint32_t hd = DM <= 0 ? 1u : 0u;
+                    S += DM;
+                    parity ^= (int)hd;
+                    if (j == 0 || fabs(DM) < best) { best = fabs(DM); amin = j; }   // first minimum
+                    bits |= hd << (j & 31);
+                    if (temp > 32 && (j & 31) == 31) {            // R1 / SPC wider than a word: spill per word
+                        X[((node * (uint32_t)temp >> 5) + (j >> 5)) * 32 + lane] = (spt == 2) ? 0u : bits;
+                        bits = 0;
+                    }
+                }
+                if (temp <= 32) {
+                    if (spt == 2) bits = (S <= 0) ? full : 0u;   // REP
+                    if (spt == 3 && parity) bits ^= 1u << amin;  // SPC: Wagner flip
+                    put_bits(dd, node, temp, bits);
+                } else {
+                    const uint32_t w0 = node * (uint32_t)temp >> 5;
+                    if (spt == 2) { const uint32_t v = (S <= 0) ? 0xffffffffu : 0u; for (int w = 0; w < (temp >> 5); ++w) X[(w0 + w) * 32 + lane] = v; }
+                    if (spt == 3 && parity) X[(w0 + (amin >> 5)) * 32 + lane] ^= 1u << (amin & 31);
+                }
+                return;
+            }
+            // one pass over the node's elements, in position order (the fp64 sums are serial in the reference):
+            //   R0  (PD/src/FastSCLLUTDecoder.cpp:83-93)   PM += (l<0)|l|
+            //   REP (:169-184)                             candidates all-0 / all-1: a0 += (l<0)|l|, a1 += (l>=0)|l|
+            //   R1  (:98-121, temp <= 32)                  hard decisions + |l| for the argsort
+            int rounds = 1;
+            uint32_t dec = 0, rowp = (uint32_t)me;
+            double a0 = PM, a1 = PM;
+            double key[32];
+            int idx[32];
+            {
+                uint32_t sw = 0;
+                for (int j = 0; j < temp; ++j) {
+                    if ((j & 7) == 0) sw = node_word(dd, j >> 3);
+                    const double l = llr_of(next_line(), nib(sw, j & 7));
+                    const double al = fabs(l);
+                    if (spt == 0) {
+                        PM += (double)(float)(l < 0) * al;
+                    } else if (spt == 2) {
+                        a0 += (double)(l < 0) * al;
+                        a1 += (double)(l >= 0) * al;
+                    } else {
+                        key[j & 31] = al;
+                        idx[j & 31] = j;
+                        dec |= (l < 0 ? 1u : 0u) << (j & 31);
+                    }
+                }
+            }
+            if (spt == 0) rounds = 0;
+            if (spt == 1) {
+                std_sort_idx(idx, temp, key);     // argsort(abs_llr) with libstdc++'s tie order, per path
+                rounds = (L - 1 < temp) ? L - 1 : temp;
+                __syncwarp();
+                for (int k = 0; k < rounds; ++k) { R1S[k * 32 + lane] = key[idx[k]]; R1Q[k * 32 + lane] = (uint32_t)idx[k]; }
+                __syncwarp();
+            }
+            for (int layer = 0; layer < rounds; ++layer) {
+                uint32_t q = 0;
+                if (spt == 1) {
+                    const int rl = gbase | (int)rowp;
+                    q = R1Q[layer * 32 + rl];
+                    a0 = PM;
+                    a1 = PM + R1S[layer * 32 + rl];
+                }
+                int p;
+                uint32_t fl;
+                fork(a0, a1, p, fl);
+                if (spt == 1) {      // the flipped position is the slot's OWN pre-permutation ordering
+                    dec = __shfl_sync(kFull, dec, p);
+                    if (fl) dec ^= 1u << q;
+                    rowp = __shfl_sync(kFull, rowp, p);
+                } else {
+                    dec = fl ? full : 0u;
+                }
+            }
+            if (temp <= 32) put_bits(dd, node, temp, dec);
+            else {                   // REP wider than a word
+                for (int w = 0; w < (temp >> 5); ++w) X[((node * (uint32_t)temp >> 5) + w) * 32 + lane] = dec;
+                if ((node & 1u) == 0) setown(pu, dd);
+                __syncwarp();
+            }
+        };
+
+        // ---- the compiled tree walk ----
+        uint2 op_next = __ldg(fp.ops);
+        for (int oi = 0; oi < fp.n_ops; ++oi) {
+            const uint2 op = op_next;
+            if (oi + 1 < fp.n_ops) op_next = __ldg(fp.ops + oi + 1);
+            const int ot = (int)(op.x & 0xffu), od = (int)((op.x >> 8) & 0xffu), oa = (int)((op.x >> 16) & 0xffu);
+            const uint32_t onode = op.y;
+            switch (ot) {
+            case FOP_UF: fg_step(od, onode, false); break;
+            case FOP_UG: fg_step(od, onode, true); break;
+            case FOP_UC: combine(od, onode); break;
+            case FOP_SP: if (FAST) special(oa, od, onode); break;
+            case FOP_SBEGIN: if (FAST) { w3 = *level_ptr(top, vslot(top)); xb = 0; w21 = 0; } break;
+            case FOP_SF3: if (FAST) {      // A.f : 8 -> 4 symbols
+                const uint32_t t = next_line();
+                uint32_t w2 = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w2 |= lut16(t, nib(w3, k), nib(w3, k + 4)) << (4 * k);
+                w21 = w2;
+                break;
+            }
+            case FOP_SG3: if (FAST) {      // A.g : u = the 4 partial sums of the left half
+                const uint32_t t0 = next_line(), t1 = next_line();
+                uint32_t w2 = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t a = nib(w3, k), b = nib(w3, k + 4);
+                    const uint32_t s0 = lut16(t0, a, b), s1 = lut16(t1, a, b);
+                    w2 |= (((xb >> k) & 1u) ? s1 : s0) << (4 * k);
+                }
+                w21 = w2;
+                break;
+            }
+            case FOP_SF2: if (FAST) {      // B.f : 4 -> 2 symbols
+                const uint32_t t = next_line();
+                const uint32_t c2 = w21 & 0xffffu;
+                const uint32_t w1 = lut16(t, nib(c2, 0), nib(c2, 2)) | (lut16(t, nib(c2, 1), nib(c2, 3)) << 4);
+                w21 = c2 | (w1 << 16);
+                break;
+            }
+            case FOP_SG2: if (FAST) {      // B.g : u = the 2 partial sums of the left pair (oa = which half of the subtree)
+                const uint32_t t0 = next_line(), t1 = next_line();
+                const uint32_t c2 = w21 & 0xffffu;
+                uint32_t w1 = 0;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t a = nib(c2, k), b = nib(c2, k + 2);
+                    const uint32_t s0 = lut16(t0, a, b), s1 = lut16(t1, a, b);
+                    w1 |= (((xb >> (4 * oa + k)) & 1u) ? s1 : s0) << (4 * k);
+                }
+                w21 = c2 | (w1 << 16);
+                break;
+            }
+            case FOP_SC2: if (FAST) xb ^= ((xb >> (4 * oa + 2)) & 3u) << (4 * oa); break;
+            case FOP_SC3: if (FAST) xb ^= (xb >> 4) & 15u; break;
+            case FOP_SEND: if (FAST) {     // publish the subtree's 8 partial sums in the lane's own slot
+                uint32_t *xo = X + ((8u * onode) >> 5) * 32 + lane;
+                const int sh = (int)((8u * onode) & 31u);
+                *xo = (*xo & ~(0xffu << sh)) | ((xb & 0xffu) << sh);
+                if (L > 1 && (onode & 1u) == 0) setown(pu, top);
+                __syncwarp();
+                break;
+            }
+            case FOP_SUB8:       // a whole plain 8-leaf subtree: 8 chunk-aligned chunks, see plan_fast_lut
+            case FOP_SPAIR: {    // one leaf pair of a subtree that contains special nodes: 5 lines
+                const bool whole = !FAST || ot == FOP_SUB8;
+                const int s = whole ? (int)onode : (int)(onode >> 2);
+                const uint32_t fz = (__ldg(fp.frozen_words + (s >> 2)) >> ((s & 3) * 8)) & 0xffu;
+                if (whole) { uq = 4; w3 = *level_ptr(top, vslot(top)); xb = 0; }
+                const int c4_end = whole ? 4 : (int)(onode & 3u) + 1;
+#pragma unroll 1
+                for (int c4 = whole ? 0 : (int)(onode & 3u); c4 < c4_end; ++c4) {
+                    const int pos = 2 * c4;
+                    uint4 c0, c1;
+                    if (whole) {
+                        c0 = next_chunk(); c1 = next_chunk();
+                        if ((c4 & 1) == 0) {
+                            uint32_t w2 = 0;
+                            if (c4 == 0) {          // A.f
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) w2 |= lut16(c0.x, nib(w3, k), nib(w3, k + 4)) << (4 * k);
+                            } else {                // A.g
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t a = nib(w3, k), b = nib(w3, k + 4);
+                                    const uint32_t s0 = lut16(c0.x, a, b), s1 = lut16(c0.y, a, b);
+                                    w2 |= (((xb >> k) & 1u) ? s1 : s0) << (4 * k);
+                                }
+                            }
+                            const uint32_t w1 = lut16(c0.z, nib(w2, 0), nib(w2, 2)) | (lut16(c0.z, nib(w2, 1), nib(w2, 3)) << 4);   // B.f
+                            w21 = w2 | (w1 << 16);
+                        } else {                    // B.g
+                            const uint32_t c2 = w21 & 0xffffu;
+                            uint32_t w1 = 0;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t a = nib(c2, k), b = nib(c2, k + 2);
+                                const uint32_t s0 = lut16(c0.x, a, b), s1 = lut16(c0.y, a, b);
+                                w1 |= (((xb >> (pos - 2 + k)) & 1u) ? s1 : s0) << (4 * k);
+                            }
+                            w21 = c2 | (w1 << 16);
+                        }
+                    } else {
+                        c0.x = c0.y = c0.z = 0;
+                        c0.w = next_line();
+                        c1.x = next_line(); c1.y = next_line(); c1.z = next_line(); c1.w = next_line();
+                    }
+#pragma unroll 1
+                    for (int side = 0; side < 2; ++side) {
+                        // leaf symbol through the depth n-1 node: f table (left leaf) or g tables with u = left leaf's bit
+                        const uint32_t w1 = w21 >> 16;
+                        const uint32_t a = nib(w1, 0), b = nib(w1, 1);
+                        uint32_t sym;
+                        if (side == 0) {
+                            sym = lut16(c0.w, a, b);
+                        } else {
+                            const uint32_t s0 = lut16(c1.y, a, b), s1 = lut16(c1.z, a, b);
+                            sym = ((xb >> pos) & 1u) ? s1 : s0;
+                        }
+                        const int lp = pos + side;
+                        const bool frozen = (fz >> lp) & 1u;
+                        // leaf decision (PD/src/SCLUTDecoder.cpp:59-67 / SCLLUTDecoder.cpp:92-145)
+                        const double DM = llr_of(side == 0 ? c1.x : c1.w, sym);
+                        uint32_t bit = 0;
+                        if (L == 1) {
+                            bit = (!frozen && DM <= 0) ? 1u : 0u;
+                        } else if (frozen) {
+                            PM += fabs(DM) * (double)(DM < 0);
+                        } else {
+                            const uint32_t dec = (DM < 0) ? 1u : 0u;
+                            int p;
+                            uint32_t fl;
+                            fork(PM, PM + fabs(DM), p, fl);
+                            bit = __shfl_sync(kFull, dec, p) ^ fl;
+                        }
+                        xb = (xb & ~(1u << lp)) | (bit << lp);
+                    }
+                    xb ^= ((xb >> (pos + 1)) & 1u) << pos;                          // combine of the depth n-1 node
+                    if (whole && (c4 & 1)) xb ^= ((xb >> pos) & 3u) << (pos - 2);   // combine of the depth n-2 node
+                }
+                if (whole) {
+                    xb ^= (xb >> 4) & 15u;                                          // combine of the subtree root
+                    uint32_t *xo = X + ((8u * s) >> 5) * 32 + lane;
+                    const int sh = (8 * s) & 31;
+                    *xo = (*xo & ~(0xffu << sh)) | ((xb & 0xffu) << sh);
+                    if (L > 1 && (s & 1) == 0) setown(pu, top);
+                    __syncwarp();
+                }
+                break;
+            }
+            default: break;
+            }
         }
 
         // ---------------- epilogue: choose the path, u = x F^{(x)n}, gather the information bits ----------------
@@ -461,23 +671,30 @@ inline bool fast_upload(FastPlan *pl, const std::vector<T> &h, const T **out) {
     return true;
 }
 
-inline const void *fast_kernel_fn(int logL, bool ca) {
+template <int LOGL>
+inline const void *fast_kernel_fn_l(bool ca, bool fast) {
+    if (LOGL == 0) return fast ? (const void *)scl_lut_warp_kernel<0, false, true> : (const void *)scl_lut_warp_kernel<0, false, false>;
+    if (ca) return fast ? (const void *)scl_lut_warp_kernel<LOGL, true, true> : (const void *)scl_lut_warp_kernel<LOGL, true, false>;
+    return fast ? (const void *)scl_lut_warp_kernel<LOGL, false, true> : (const void *)scl_lut_warp_kernel<LOGL, false, false>;
+}
+inline const void *fast_kernel_fn(int logL, bool ca, bool fast) {
     switch (logL) {
-    case 0: return (const void *)scl_lut_warp_kernel<0, false>;
-    case 1: return ca ? (const void *)scl_lut_warp_kernel<1, true> : (const void *)scl_lut_warp_kernel<1, false>;
-    case 2: return ca ? (const void *)scl_lut_warp_kernel<2, true> : (const void *)scl_lut_warp_kernel<2, false>;
-    default: return ca ? (const void *)scl_lut_warp_kernel<3, true> : (const void *)scl_lut_warp_kernel<3, false>;
+    case 0: return fast_kernel_fn_l<0>(false, fast);
+    case 1: return fast_kernel_fn_l<1>(ca, fast);
+    case 2: return fast_kernel_fn_l<2>(ca, fast);
+    default: return fast_kernel_fn_l<3>(ca, fast);
     }
 }
 
-// Decide whether the specialised kernel applies and build its table stream (consumption order!).
-// kind_* are the pd_kind values of the three eligible classes.
-inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kind_cascllut,
+// Decide whether the specialised kernel applies; if so compile the reference's tree walk into the op list and
+// lay the tables out as one stream in consumption order.
+//   node_type / max_special: Fast kinds only (max_special = 2 for the list decoders, 3 for FastSCLUT, -1 otherwise)
+inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_type, int max_special,
                           const std::vector<NodeTab> &tabs, const std::vector<uint8_t> &pool,
                           const std::vector<double> &llr, const std::vector<uint32_t> &llr_off,
                           const int64_t *llr_off64, const int32_t *frozen, uint32_t crc_taps, FastPlan *pl) {
     pl->ok = false;
-    if (d.kind != kind_sclut && d.kind != kind_scllut && d.kind != kind_cascllut) return;
+    if (!eligible_kind) return;
     const int N = d.N, n = d.n, L = d.list ? d.L : 1;
     if (N < 32) return;
     int logL = 0;
@@ -488,10 +705,11 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
         if (t.f_pstride || t.g_pstride) return;
         if (t.f_qb > 16 || t.g_qb > 16 || t.f_sz / t.f_qb > 16 || t.g_sz / t.g_qb > 16) return;
     }
-    for (int leaf = 0; leaf < N; ++leaf) {
-        int64_t r = (int64_t)(n - 1) * N + leaf;
-        if (llr_off64[r + 1] - llr_off64[r] > 16) return;
-    }
+    auto is_special = [&](int depth, int node) -> int {   // -1 or the special type
+        if (max_special < 0 || depth >= n) return -1;
+        int t = node_type[(1 << depth) + node - 1];
+        return (t >= 0 && t <= max_special) ? t : -1;
+    };
     // ---- the stream, in the exact order scl_lut_warp_kernel consumes it ----
     std::vector<uint32_t> stream;
     auto push_table = [&](uint32_t off, int qa, int qb) {
@@ -509,44 +727,91 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
         push_table(tabs[p].g_off, tabs[p].g_sz / tabs[p].g_qb, tabs[p].g_qb);
         push_table(tabs[p].g_off + tabs[p].g_sz, tabs[p].g_sz / tabs[p].g_qb, tabs[p].g_qb);
     };
-    auto push_llr = [&](int leaf) {
+    // The walk (same recursion as the reference's state machine) emits ops and, in the same
+    // order, the lines each op consumes:
+    //   UF: f | UG: g0 g1 | SP: one LLR line per element (none for the non-list R0) | SF3/SF2: f | SG3/SG2: g0 g1
+    //   SPAIR: C.f llr(left) C.g0 C.g1 llr(right)
+    //   SUB8 (chunk aligned): per leaf pair c4 two chunks [P0 P1 P2 C.f] [llr C.g0 C.g1 llr] with
+    //        (P0,P1,P2) = (A.f,-,B.f) for c4=0, (A.g0,A.g1,B.f) for c4=2, (B.g0,B.g1,-) for c4 odd
+    const int top = n - 3;
+    auto heap = [&](int depth, int node) { return (1 << depth) + node - 1; };
+    auto push_pad = [&]() { stream.insert(stream.end(), 32, 0u); };
+    std::vector<uint2> ops;
+    auto emit = [&](uint32_t type, int depth, int arg, uint32_t node) {
+        ops.push_back(make_uint2(type | ((uint32_t)depth << 8) | ((uint32_t)arg << 16), node));
+    };
+    bool ok = true, has_r1 = false;
+    auto push_llr_row = [&](int level, int pos) {
+        int64_t r = (int64_t)level * N + pos;
+        int len = (int)(llr_off64[r + 1] - llr_off64[r]);
+        if (len > 16) { ok = false; len = 16; }
         uint32_t line[32];
         memset(line, 0, sizeof line);
-        int64_t r = (int64_t)(n - 1) * N + leaf;
-        int len = (int)(llr_off64[r + 1] - llr_off64[r]);
         memcpy(line, &llr[llr_off[r]], (size_t)len * sizeof(double));
         stream.insert(stream.end(), line, line + 32);
     };
-    // one stream, in the exact order the kernel consumes it: per 8-leaf subtree s
-    //   [g of the ancestor at depth top-1-ctz(s)] [f chain down to depth top-1]      padded to a 4-line chunk
-    //   then per leaf pair c4 two chunks: [P0 P1 P2 C.f] [llr(left) C.g0 C.g1 llr(right)] with
-    //   (P0,P1,P2) = (A.f,-,B.f) for c4=0, (A.g0,A.g1,B.f) for c4=2, (B.g0,B.g1,-) for c4 odd
-    const int top = n - 3, NS = N >> 3;
-    auto heap = [&](int depth, int node) { return (1 << depth) + node - 1; };
-    auto push_pad = [&]() { stream.insert(stream.end(), 32, 0u); };
-    for (int sidx = 0; sidx < NS; ++sidx) {
-        int dstart = 0;
-        if (sidx != 0) {
-            int t = __builtin_ctz((unsigned)sidx);
-            int dg = top - 1 - t;
-            push_g(heap(dg, sidx >> (t + 1)));
-            dstart = dg + 1;
+    std::function<bool(int, int)> plain = [&](int depth, int node) -> bool {   // no special node in this subtree
+        if (depth >= n) return true;
+        if (is_special(depth, node) >= 0) return false;
+        return plain(depth + 1, 2 * node) && plain(depth + 1, 2 * node + 1);
+    };
+    std::function<void(int, int)> walk = [&](int depth, int node) {
+        const int p = heap(depth, node), temp = N >> depth;
+        const int st = is_special(depth, node);
+        if (st >= 0) {
+            if (L > 1 && st == 1) { has_r1 = true; if (temp > 32) ok = false; }
+            emit(FOP_SP, depth, st, (uint32_t)node);
+            if (!(L == 1 && st == 0))
+                for (int j = 0; j < temp; ++j) push_llr_row(depth - 1, node * temp + j);
+            return;
         }
-        for (int dd = dstart; dd <= top - 1; ++dd) push_f(heap(dd, sidx >> (top - dd)));
-        while ((stream.size() / 32) % 4) push_pad();
-        const int A = heap(top, sidx);
-        for (int c4 = 0; c4 < 4; ++c4) {
-            const int Bn = heap(top + 1, 2 * sidx + (c4 >> 1));
-            if (c4 == 0) { push_f(A); push_pad(); push_f(Bn); }
-            else if (c4 == 2) { push_g(A); push_f(Bn); }
-            else { push_g(Bn); push_pad(); }
-            const int Cn = heap(top + 2, 4 * sidx + c4), leaf0 = 8 * sidx + 2 * c4;
-            push_f(Cn);
-            push_llr(leaf0);
-            push_g(Cn);
-            push_llr(leaf0 + 1);
+        if (depth < top) {
+            emit(FOP_UF, depth, 0, (uint32_t)node); push_f(p);
+            walk(depth + 1, 2 * node);
+            emit(FOP_UG, depth, 0, (uint32_t)node); push_g(p);
+            walk(depth + 1, 2 * node + 1);
+            emit(FOP_UC, depth, 0, (uint32_t)node);
+        } else if (depth == top) {
+            if (plain(depth, node)) {
+                while ((stream.size() / 32) % 4) push_pad();
+                emit(FOP_SUB8, depth, 0, (uint32_t)node);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int Bn = heap(top + 1, 2 * node + (c4 >> 1));
+                    if (c4 == 0) { push_f(p); push_pad(); push_f(Bn); }
+                    else if (c4 == 2) { push_g(p); push_f(Bn); }
+                    else { push_g(Bn); push_pad(); }
+                    const int Cn = heap(top + 2, 4 * node + c4), leaf0 = 8 * node + 2 * c4;
+                    push_f(Cn);
+                    push_llr_row(n - 1, leaf0);
+                    push_g(Cn);
+                    push_llr_row(n - 1, leaf0 + 1);
+                }
+            } else {
+                emit(FOP_SBEGIN, depth, 0, (uint32_t)node);
+                emit(FOP_SF3, depth, 0, (uint32_t)node); push_f(p);
+                walk(depth + 1, 2 * node);
+                emit(FOP_SG3, depth, 0, (uint32_t)node); push_g(p);
+                walk(depth + 1, 2 * node + 1);
+                emit(FOP_SC3, depth, 0, (uint32_t)node);
+                emit(FOP_SEND, depth, 0, (uint32_t)node);
+            }
+        } else if (depth == top + 1) {
+            const int m = node & 1;
+            emit(FOP_SF2, depth, m, (uint32_t)node); push_f(p);
+            walk(depth + 1, 2 * node);
+            emit(FOP_SG2, depth, m, (uint32_t)node); push_g(p);
+            walk(depth + 1, 2 * node + 1);
+            emit(FOP_SC2, depth, m, (uint32_t)node);
+        } else {   // depth == top + 2 == n - 1: an ordinary leaf pair; node = 4*s + c4
+            emit(FOP_SPAIR, depth, 0, (uint32_t)node);
+            push_f(p);
+            push_llr_row(n - 1, 2 * node);
+            push_g(p);
+            push_llr_row(n - 1, 2 * node + 1);
         }
-    }
+    };
+    walk(0, 0);
+    if (!ok) return;
     // pad to whole chunks of 4 lines and transpose each chunk to [lane][4]
     while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
     const int n_lines = (int)(stream.size() / 32);
@@ -563,7 +828,7 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
     if (P.n_chunks < 1) return;
     std::vector<uint32_t> fw((N + 31) / 32, 0);
     for (int i = 0; i < N; ++i) if (frozen[i] == 1) fw[i >> 5] |= 1u << (i & 31);
-    if (!fast_upload(pl, stream, &P.stream) || !fast_upload(pl, fw, &P.frozen_words)) { free_fast_plan(pl); return; }
+    if (!fast_upload(pl, stream, &P.stream) || !fast_upload(pl, fw, &P.frozen_words) || !fast_upload(pl, ops, &P.ops)) { free_fast_plan(pl); return; }
     if (d.ca) {
         // remainder of the unit message e_k under the reference's long division (utils.cpp:77-93): linear, so the
         // CRC of a word is the XOR of the remainders of its set bits
@@ -598,12 +863,15 @@ inline void plan_fast_lut(const Dev &d, int kind_sclut, int kind_scllut, int kin
     P.vwords = std::max(soff, 1);
     P.xwords = N / 32;
     P.scrwords = (L == 1) ? 0 : (N / 32) * FPW;
-    size_t words = (size_t)P.vwords * 32 + (size_t)P.xwords * 32 + (size_t)P.scrwords + kRingChunks * 128 + 128 + 32;
+    P.n_ops = (int)ops.size();
+    P.r1_words = has_r1 ? 7 * 32 * 3 : 0;
+    size_t words = (size_t)P.vwords * 32 + (size_t)P.xwords * 32 + (size_t)P.scrwords + kRingChunks * 128 + 128 + 32 + P.r1_words;
     pl->smem = words * 4;
     pl->ws_bytes_per_cta = (size_t)P.gwords * 32 * 4;
     pl->logL = logL;
     pl->ca = d.ca != 0;
-    const void *fn = fast_kernel_fn(logL, pl->ca);
+    pl->fastk = max_special >= 0;
+    const void *fn = fast_kernel_fn(logL, pl->ca, pl->fastk);
     if (pl->smem > 200 * 1024) { free_fast_plan(pl); return; }
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess) { cudaGetLastError(); free_fast_plan(pl); return; }
     int occ = 0;
@@ -622,14 +890,10 @@ inline int fast_grid(const FastPlan &pl, long long B, int sm_count) {
 inline int launch_fast_lut(const Dev &d, const FastPlan &pl, const void *d_in, int dtype, long long B, uint8_t *d_out,
                            cudaStream_t s, uint32_t *ws, int *d_err, double *dbg_pm, int *dbg_win, int sm_count) {
     const int grid = fast_grid(pl, B, sm_count);
-#define PB_LAUNCH(LOGL, CAF) scl_lut_warp_kernel<LOGL, CAF><<<grid, 32, pl.smem, s>>>(d, pl.p, d_in, dtype, d_out, B, ws, d_err, dbg_pm, dbg_win)
-    switch (pl.logL) {
-    case 0: PB_LAUNCH(0, false); break;
-    case 1: if (pl.ca) PB_LAUNCH(1, true); else PB_LAUNCH(1, false); break;
-    case 2: if (pl.ca) PB_LAUNCH(2, true); else PB_LAUNCH(2, false); break;
-    default: if (pl.ca) PB_LAUNCH(3, true); else PB_LAUNCH(3, false); break;
-    }
-#undef PB_LAUNCH
+    void *args[] = {(void *)&d, (void *)&pl.p, (void *)&d_in, (void *)&dtype, (void *)&d_out, (void *)&B, (void *)&ws,
+                    (void *)&d_err, (void *)&dbg_pm, (void *)&dbg_win};
+    cudaError_t e = cudaLaunchKernel(fast_kernel_fn(pl.logL, pl.ca, pl.fastk), dim3(grid), dim3(32), args, pl.smem, s);
+    if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }
 

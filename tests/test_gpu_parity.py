@@ -63,6 +63,15 @@ BIG = [
     ("SCLLUTDecoder", dict(N=1024, K=512, L=8, B=300)),
     ("SCLUTDecoder", dict(N=1024, K=512, B=1000)),
     ("CAFastSCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, B=200)),
+    ("FastSCLLUTDecoder", dict(N=1024, K=768, L=8, B=100)),       # high rate: R1 nodes > 32 leaves -> generic kernel
+    ("FastSCLLUTDecoder", dict(N=1024, K=512, L=4, B=200)),
+    ("FastSCLLUTDecoder", dict(N=256, K=64, L=2, B=500)),
+    ("FastSCLUTDecoder", dict(N=1024, K=700, B=1000)),            # wide R1 / SPC nodes in the non-list warp path
+    ("FastSCLUTDecoder", dict(N=64, K=40, B=1000)),
+    ("SCLUTDecoder", dict(N=32, K=16, B=1000)),
+    ("SCLLUTDecoder", dict(N=32, K=16, L=8, B=1000)),
+    ("SCLLUTDecoder", dict(N=2048, K=1024, L=8, B=60, construction="pw")),
+    ("SCLLUTDecoder", dict(N=4096, K=2048, L=4, B=30, construction="pw")),
 ]
 
 
@@ -78,7 +87,10 @@ def test_cuda_matches_oracle(q, kind, ckw, tables):
     assert bad == 0, f"{bad}/{x.shape[0]} frames differ from the oracle ({dec.kernel})"
 
 
-@pytest.mark.parametrize("kind,ckw", [b for b in BIG if b[0] in ("SCLUTDecoder", "SCLLUTDecoder", "CASCLLUTDecoder")][:6],
+_WARP_KINDS = ("SCLUTDecoder", "SCLLUTDecoder", "CASCLLUTDecoder", "FastSCLUTDecoder", "FastSCLLUTDecoder", "CAFastSCLLUTDecoder")
+
+
+@pytest.mark.parametrize("kind,ckw", [b for b in BIG if b[0] in _WARP_KINDS and b[1]["N"] <= 512],
                          ids=lambda v: v if isinstance(v, str) else f"N{v['N']}-L{v.get('L', 1)}")
 def test_generic_kernel_still_covers_the_fast_kernels_classes(q, kind, ckw, monkeypatch):
     """The specialised warp kernel takes over the LUT SC/SCL classes; the schedule-driven generic kernel must
