@@ -20,6 +20,7 @@
 #include "pb_internal.h"
 #include "pb_generic.cuh"
 #include "pb_scl_lut.cuh"
+#include "pb_path_warp.cuh"
 
 using namespace pb;
 
@@ -83,6 +84,8 @@ struct pd_decoder {
     int ctas_per_sm = 1;
     // specialised kernel
     FastPlan fast{};
+    PathPlan path{};          // warp-level schedule interpreter (all classes, L power of two)
+    int force = 0;            // POLAR_B200_FORCE_GENERIC: 1 = CTA-per-frame generic kernel, 2 = path_warp
     const char *kernel_name = "generic";
     int *d_err = nullptr;
     double *dbg_pm = nullptr;
@@ -91,7 +94,6 @@ struct pd_decoder {
     size_t ws_user_cap = 0;
     StreamSlot slot[2];
     int64_t chunk_frames = 0;
-    bool force_generic = false;
 };
 
 namespace {
@@ -302,7 +304,10 @@ int plan_generic(pd_decoder *D) {
 
 size_t ws_need(const pd_decoder *D, int dtype, const void *d_in, int64_t B);
 bool want_fast(const pd_decoder *D, int dtype, const void *d_in) {
-    return D->fast.ok && dtype != PD_F64 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && !D->force_generic;
+    return D->fast.ok && dtype != PD_F64 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && D->force == 0;
+}
+bool want_path(const pd_decoder *D, int dtype, const void *d_in) {
+    return !want_fast(D, dtype, d_in) && D->path.ok && D->force != 1;
 }
 
 int launch(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws) {
@@ -313,12 +318,19 @@ int launch(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out
         if (rc != 0) return fail(PD_ECUDA, "fast kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         return PD_OK;
     }
+    if (want_path(D, dtype, d_in)) {
+        int rc = launch_path_warp(D->dev, D->path, d_in, dtype, B, d_out, s, ws, D->d_err, D->dbg_pm, D->dbg_win, D->sm_count);
+        g_launches++;
+        if (rc != 0) return fail(PD_ECUDA, "path_warp launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        return PD_OK;
+    }
     return launch_generic(D, d_in, dtype, B, d_out, s, ws);
 }
 
 // bytes of global workspace the kernel chosen for this call needs
 size_t ws_need(const pd_decoder *D, int dtype, const void *d_in, int64_t B) {
     if (want_fast(D, dtype, d_in)) return D->fast.ws_bytes_per_cta * (size_t)fast_grid(D->fast, B, D->sm_count);
+    if (want_path(D, dtype, d_in)) return D->path.ws_bytes_per_cta * (size_t)path_grid(D->path, B, D->sm_count);
     return D->use_smem ? 0 : D->ws_bytes * (size_t)generic_grid(D, B);
 }
 
@@ -453,8 +465,9 @@ int pd_create(const pd_config *c, pd_decoder **out) {
         cudaMemset(p, 0, sizeof(int));
     }
     if ((rc = plan_generic(D))) return bail(rc);
-    if (const char *e = getenv("POLAR_B200_FORCE_GENERIC")) D->force_generic = e[0] == '1';
-    D->kernel_name = (D->fast.ok && !D->force_generic) ? D->fast.name : "generic";
+    plan_path_warp(D->dev, &D->path);
+    if (const char *e = getenv("POLAR_B200_FORCE_GENERIC")) D->force = atoi(e);
+    D->kernel_name = (D->fast.ok && D->force == 0) ? D->fast.name : (D->path.ok && D->force != 1) ? "path_warp" : "generic";
     // frames per pipeline chunk of pd_decode: ~32 MB of input per chunk
     size_t in_frame = (size_t)N * (d.domain == DOM_LUT ? 4 : 8);
     D->chunk_frames = std::max<int64_t>(1024, (int64_t)((32u << 20) / in_frame));

@@ -103,6 +103,28 @@ def test_generic_kernel_still_covers_the_fast_kernels_classes(q, kind, ckw, monk
     assert (dec.decode(x) == want).all()
 
 
+@pytest.mark.parametrize("force,kernel", [("1", "generic"), ("2", "path_warp")])
+@pytest.mark.parametrize("kind,ckw", [
+    ("SCDecoder", dict(N=128, K=64, B=500)), ("FastSCDecoder", dict(N=256, K=128, B=500)),
+    ("SCLDecoder", dict(N=128, K=64, L=8, B=300)), ("FastSCLDecoder", dict(N=256, K=150, L=8, B=300)),
+    ("CASCLDecoder", dict(N=128, K=64, L=4, A=40, B=300)), ("SCLUniformQuantizedDecoder", dict(N=128, K=64, L=16, B=100)),
+    ("SCLLloydQuantizedDecoder", dict(N=128, K=64, L=32, B=60)), ("SCLLUTDecoder", dict(N=256, K=128, L=32, B=60)),
+    ("FastSCLLUTDecoder", dict(N=512, K=384, L=16, B=60)), ("CAFastSCLLUTDecoder", dict(N=256, K=152, A=128, L=8, B=200)),
+    ("FastSCLUTDecoder", dict(N=256, K=128, B=500)), ("CASCLLUTDecoder", dict(N=128, K=64, A=40, L=2, B=300)),
+], ids=lambda v: v if isinstance(v, str) else f"N{v['N']}-L{v.get('L', 1)}")
+def test_both_schedule_interpreters(q, kind, ckw, force, kernel, monkeypatch):
+    """The CTA-per-frame generic kernel and the warp-level path kernel interpret the same schedule; both must be
+    bit-exact for every class (whichever one a given shape is routed to by default)."""
+    monkeypatch.setenv("POLAR_B200_FORCE_GENERIC", force)
+    kw, x, _ = common.make_case(kind, seed=79, **ckw)
+    dec = _build(q, kind, kw)
+    assert dec.kernel == kernel
+    want = po.OracleDecoder(kind, **kw).decode(x)
+    got = dec.decode(x)
+    bad = int((got != want).any(axis=1).sum())
+    assert bad == 0, f"{bad}/{x.shape[0]} frames differ ({dec.kernel})"
+
+
 def test_reference_call_conventions(q):
     """(N,), (1,N), float64 symbols (forcecast like py::array_t<int>), uint8 fast path, batch of one."""
     kw, x, _ = common.make_case("SCLLUTDecoder", N=128, K=32, L=8, B=8, seed=3)
