@@ -20,12 +20,12 @@ SHAPES = [
     ("NS SCL-LUT N=1024 A=512 L=8 Q=16", "SCLLUTDecoder", dict(N=1024, K=512, L=8, tables="minsum"), 1 << 17),
     ("SC-LUT N=1024 A=512", "SCLUTDecoder", dict(N=1024, K=512, tables="minsum"), 1 << 18),
     ("CASCL-LUT N=1024 A=512 L=8", "CASCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, tables="minsum"), 1 << 17),
-    ("C4 CAFastSCL-LUT N=1024 A=512 L=8", "CAFastSCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, tables="minsum"), 1 << 14),
-    ("FastSC-LUT N=1024 A=512", "FastSCLUTDecoder", dict(N=1024, K=512, tables="minsum"), 1 << 16),
-    ("float SCL N=1024 A=512 L=8", "SCLDecoder", dict(N=1024, K=512, L=8, tables="channel"), 1 << 13),
-    ("float FastSCL N=1024 A=512 L=8", "FastSCLDecoder", dict(N=1024, K=512, L=8, tables="channel"), 1 << 13),
-    ("C5 SCL-Uniform N=2048 A=1024 L=32 v=16", "SCLUniformQuantizedDecoder", dict(N=2048, K=1024, L=32, construction="pw"), 1 << 10),
-    ("SCL-Lloyd N=1024 A=512 L=8", "SCLLloydQuantizedDecoder", dict(N=1024, K=512, L=8), 1 << 12),
+    ("C4 CAFastSCL-LUT N=1024 A=512 L=8", "CAFastSCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, tables="minsum"), 1 << 17),
+    ("FastSC-LUT N=1024 A=512", "FastSCLUTDecoder", dict(N=1024, K=512, tables="minsum"), 1 << 18),
+    ("float SCL N=1024 A=512 L=8", "SCLDecoder", dict(N=1024, K=512, L=8, tables="channel"), 1 << 16),
+    ("float FastSCL N=1024 A=512 L=8", "FastSCLDecoder", dict(N=1024, K=512, L=8, tables="channel"), 1 << 16),
+    ("C5 SCL-Uniform N=2048 A=1024 L=32 v=16", "SCLUniformQuantizedDecoder", dict(N=2048, K=1024, L=32, construction="pw"), 1 << 13),
+    ("SCL-Lloyd N=1024 A=512 L=8", "SCLLloydQuantizedDecoder", dict(N=1024, K=512, L=8), 1 << 15),
 ]
 
 
