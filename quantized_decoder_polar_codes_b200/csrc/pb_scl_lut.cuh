@@ -111,12 +111,15 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     //      is consumed exactly once per pass, in a fixed order, and lane l only ever needs word l of a line.  The
     //      host lays the lines out in consumption order, 4 lines per lane-transposed 512-byte chunk, and each
     //      lane streams ITS 16 bytes of every chunk with cp.async into a private ring (no cross-lane sync). ----
-    int fetch_chunk = 0;    // stream position of the next chunk to prefetch
-    unsigned chunk_no = 0;  // chunks consumed so far
-    const uint4 *stream4 = reinterpret_cast<const uint4 *>(fp.stream) + lane;
+    unsigned fetch_off = 0;            // byte offset (within the stream) of the next chunk to prefetch
+    unsigned chunk_no = 0;             // chunks consumed so far
+    const unsigned stream_bytes = (unsigned)fp.n_chunks * 512u;
+    const char *stream_lane = reinterpret_cast<const char *>(fp.stream) + lane * 16;
+    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(RING + lane * 4);   // this lane's 16 bytes of slot 0
     auto issue_chunk = [&](unsigned slot) {
-        cp_async16(&RING[slot * 128 + lane * 4], stream4 + (size_t)fetch_chunk * 32);
-        fetch_chunk = (fetch_chunk + 1 == fp.n_chunks) ? 0 : fetch_chunk + 1;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(ring_lane + slot * 512u), "l"(stream_lane + fetch_off));
+        fetch_off += 512u;
+        if (fetch_off == stream_bytes) fetch_off = 0;
     };
     for (int i = 0; i < kRingChunks - 1; ++i) issue_chunk(i);
     auto next_chunk = [&]() -> uint4 {
@@ -124,7 +127,9 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         issue_chunk((slot + kRingChunks - 1) & (kRingChunks - 1));   // refill the slot consumed before this one
         cp_async_wait<kRingChunks - 1>();                            // ... and make sure this chunk has landed
         ++chunk_no;
-        return *reinterpret_cast<const uint4 *>(&RING[slot * 128 + lane * 4]);
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_lane + slot * 512u));
+        return v;
     };
     // upper-level steps take their 1 or 2 lines one at a time out of the current chunk
     uint4 ucur = make_uint4(0, 0, 0, 0);
@@ -134,6 +139,35 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         const uint32_t v = uq == 0 ? ucur.x : uq == 1 ? ucur.y : uq == 2 ? ucur.z : ucur.w;
         ++uq;
         return v;
+    };
+    // eight f (or g) lookups for one word of symbols: out nibble k = T[u_k][a_k][b_k] with a_k / b_k nibble k of A / Bv.
+    // Even and odd nibbles are split into byte lanes so that shuffle sources (a*2 + b>>3) and nibble shifts ((b&7)*4)
+    // of four elements come out of a handful of word-wide ops; SHFL only looks at the low 5 bits of its source lane
+    // and the funnel shift at the low 5 bits of its amount, so a plain >>8i isolates element i.
+    auto lookup8 = [&](uint32_t A, uint32_t Bv, uint32_t ub, uint32_t t0, uint32_t t1, auto isg_c) -> uint32_t {
+        constexpr bool ISG = decltype(isg_c)::value;
+        const uint32_t m4 = 0x0f0f0f0fu;
+        const uint32_t Ae = A & m4, Ao = (A >> 4) & m4, Be = Bv & m4, Bo = (Bv >> 4) & m4;
+        const uint32_t Se = (Ae << 1) | ((Be >> 3) & 0x01010101u), So = (Ao << 1) | ((Bo >> 3) & 0x01010101u);
+        const uint32_t He = (Be & 0x07070707u) << 2, Ho = (Bo & 0x07070707u) << 2;
+        uint32_t accE = 0, accO = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t sel = i == 0 ? 0x3214u : i == 1 ? 0x3240u : i == 2 ? 0x3410u : 0x4210u;
+            uint32_t we = __shfl_sync(kFull, t0, (int)(Se >> (8 * i)));
+            uint32_t wo = __shfl_sync(kFull, t0, (int)(So >> (8 * i)));
+            if (ISG) {
+                const uint32_t we1 = __shfl_sync(kFull, t1, (int)(Se >> (8 * i)));
+                const uint32_t wo1 = __shfl_sync(kFull, t1, (int)(So >> (8 * i)));
+                const uint32_t me_ = (uint32_t)((int)(ub << (31 - 2 * i)) >> 31);
+                const uint32_t mo_ = (uint32_t)((int)(ub << (30 - 2 * i)) >> 31);
+                we = (we & ~me_) | (we1 & me_);
+                wo = (wo & ~mo_) | (wo1 & mo_);
+            }
+            accE = __byte_perm(accE, __funnelshift_r(we, 0u, He >> (8 * i)), sel);
+            accO = __byte_perm(accO, __funnelshift_r(wo, 0u, Ho >> (8 * i)), sel);
+        }
+        return (accE & m4) | ((accO & m4) << 4);
     };
     auto lut16 = [&](uint32_t treg, uint32_t a, uint32_t b) -> uint32_t {
         const uint32_t w = __shfl_sync(kFull, treg, a * 2 + (b >> 3));
@@ -203,24 +237,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             for (int w = 0; w < nw; ++w) {
                 uint32_t An = 0, Bn = 0, un = 0;
                 if (w + 1 < nw) { An = getA(w + 1); Bn = getB(w + 1); un = getU(w + 1); }
-                uint32_t o = 0;
-                if (!isg) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t a = (A >> (4 * k)) & 15u, b = (Bv >> (4 * k)) & 15u;
-                        const uint32_t wv = __shfl_sync(kFull, t0, a * 2 + (b >> 3));
-                        o |= ((wv >> ((b & 7u) * 4)) & 15u) << (4 * k);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t a = (A >> (4 * k)) & 15u, b = (Bv >> (4 * k)) & 15u;
-                        const uint32_t sl = a * 2 + (b >> 3);
-                        const uint32_t wv0 = __shfl_sync(kFull, t0, sl), wv1 = __shfl_sync(kFull, t1, sl);
-                        const uint32_t wv = ((ub >> k) & 1u) ? wv1 : wv0;
-                        o |= ((wv >> ((b & 7u) * 4)) & 15u) << (4 * k);
-                    }
-                }
+                const uint32_t o = isg ? lookup8(A, Bv, ub, t0, t1, std::true_type{}) : lookup8(A, Bv, 0u, t0, t0, std::false_type{});
                 dst[w * 32] = o;
                 A = An; Bv = Bn; ub = un;
             }
@@ -271,9 +288,28 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
 #pragma unroll
             for (int j = 0; j < L; ++j) {
                 const double2 kf = *reinterpret_cast<const double2 *>(&KS[(gbase + j) * 2]);
-                const bool jb = j < me;
-                r0 += (jb ? !(K0 < kf.x) : (kf.x < K0)) + (kf.y < K0);
-                r1 += !(K1 < kf.x) + (jb ? !(K1 < kf.y) : (kf.y < K1));
+                // r0 += (keep_j,j) < (K0,me)  +  flip_j < K0 ;  r1 += keep_j <= K1  +  (flip_j,j) < (K1,me)
+                // (predicated adds: the compiler's bool->int lowering of the same expression costs 40 % more issue slots)
+                asm("{\n"
+                    " .reg .pred lt0, le0, f0, le1, lt1, lf1, jb, t0, t1;\n"
+                    " setp.lt.s32 jb, %6, %7;\n"
+                    " setp.lt.f64 lt0, %2, %4;\n"
+                    " setp.le.f64 le0, %2, %4;\n"
+                    " setp.lt.f64 f0, %3, %4;\n"
+                    " setp.le.f64 le1, %2, %5;\n"
+                    " setp.lt.f64 lt1, %3, %5;\n"
+                    " setp.le.f64 lf1, %3, %5;\n"
+                    " and.pred t0, jb, le0;\n"
+                    " or.pred t0, t0, lt0;\n"
+                    " and.pred t1, jb, lf1;\n"
+                    " or.pred t1, t1, lt1;\n"
+                    " @t0 add.s32 %0, %0, 1;\n"
+                    " @f0 add.s32 %0, %0, 1;\n"
+                    " @le1 add.s32 %1, %1, 1;\n"
+                    " @t1 add.s32 %1, %1, 1;\n"
+                    "}\n"
+                    : "+r"(r0), "+r"(r1)
+                    : "d"(kf.x), "d"(kf.y), "d"(K0), "d"(K1), "r"(j), "r"(me));
             }
             if (r0 < L) SEL[gbase + r0] = (uint32_t)me;
             if (r1 < L) SEL[gbase + r1] = (uint32_t)me | 16u;
