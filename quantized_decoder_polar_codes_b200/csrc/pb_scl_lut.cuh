@@ -46,8 +46,8 @@ struct FastParams {
     const uint32_t *stream;        // table stream in consumption order: [chunk][lane][4 lines' word of that lane]
     int n_chunks;
     const uint32_t *frozen_words;  // frozen mask, 32 leaves per word
-    const uint2 *ops;              // compiled tree walk: x = type | depth<<8 | arg<<16, y = node
-    int n_ops;
+    int n_ops;                     // compiled tree walk; the ops travel inside the stream (one line per 16 ops):
+                                   // x = type | depth<<8 | arg<<16, y = node
     int r1_words;                  // shared-memory words for the R1 scratch (0 when the code has no R1 node)
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
@@ -79,6 +79,8 @@ template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory");
 }
+
+__device__ __noinline__ void sort_idx_noinline(int *idx, int n, const double *key) { std_sort_idx(idx, n, key); }
 
 // 4 symbol bytes -> 4 nibbles (16 bits)
 __device__ __forceinline__ uint32_t pack4(uint32_t x) {
@@ -423,10 +425,28 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             }
             if (spt == 0) rounds = 0;
             if (spt == 1) {
-                std_sort_idx(idx, temp, key);     // argsort(abs_llr) with libstdc++'s tie order, per path
+                // argsort(abs_llr) in libstdc++'s order; only its first min(L-1,temp) entries are ever used
                 rounds = (L - 1 < temp) ? L - 1 : temp;
                 __syncwarp();
-                for (int k = 0; k < rounds; ++k) { R1S[k * 32 + lane] = key[idx[k]]; R1Q[k * 32 + lane] = (uint32_t)idx[k]; }
+                if (temp <= 16) {
+                    // <= 16 elements: std::sort is an insertion sort = stable, so entry k is the k-th smallest by
+                    // (value, index): repeated min extraction with independent loads instead of a dependent sort chain
+                    uint32_t taken = 0;
+                    for (int k = 0; k < rounds; ++k) {
+                        double best = 0;
+                        int bj = -1;
+                        for (int j = 0; j < temp; ++j) {
+                            const double kj = key[j];
+                            if (!((taken >> j) & 1u) && (bj < 0 || kj < best)) { best = kj; bj = j; }
+                        }
+                        taken |= 1u << bj;
+                        R1S[k * 32 + lane] = best;
+                        R1Q[k * 32 + lane] = (uint32_t)bj;
+                    }
+                } else {
+                    sort_idx_noinline(idx, temp, key);
+                    for (int k = 0; k < rounds; ++k) { R1S[k * 32 + lane] = key[idx[k]]; R1Q[k * 32 + lane] = (uint32_t)idx[k]; }
+                }
                 __syncwarp();
             }
             for (int layer = 0; layer < rounds; ++layer) {
@@ -457,12 +477,11 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         };
 
         // ---- the compiled tree walk ----
-        uint2 op_next = __ldg(fp.ops);
+        uint32_t opl = 0;   // this lane's word of the current op line (16 ops)
         for (int oi = 0; oi < fp.n_ops; ++oi) {
-            const uint2 op = op_next;
-            if (oi + 1 < fp.n_ops) op_next = __ldg(fp.ops + oi + 1);
-            const int ot = (int)(op.x & 0xffu), od = (int)((op.x >> 8) & 0xffu), oa = (int)((op.x >> 16) & 0xffu);
-            const uint32_t onode = op.y;
+            if ((oi & 15) == 0) opl = next_line();
+            const uint32_t opx = __shfl_sync(kFull, opl, 2 * (oi & 15)), onode = __shfl_sync(kFull, opl, 2 * (oi & 15) + 1);
+            const int ot = (int)(opx & 0xffu), od = (int)((opx >> 8) & 0xffu), oa = (int)((opx >> 16) & 0xffu);
             switch (ot) {
             case FOP_UF: fg_step(od, onode, false); break;
             case FOP_UG: fg_step(od, onode, true); break;
@@ -773,8 +792,12 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     auto heap = [&](int depth, int node) { return (1 << depth) + node - 1; };
     auto push_pad = [&]() { stream.insert(stream.end(), 32, 0u); };
     std::vector<uint2> ops;
+    std::vector<std::vector<uint32_t>> op_lines;   // the lines each op consumes, in order
     auto emit = [&](uint32_t type, int depth, int arg, uint32_t node) {
+        if (!ops.empty()) op_lines.back().swap(stream);   // `stream` collects the lines of the op being emitted
+        stream.clear();
         ops.push_back(make_uint2(type | ((uint32_t)depth << 8) | ((uint32_t)arg << 16), node));
+        op_lines.emplace_back();
     };
     bool ok = true, has_r1 = false;
     auto push_llr_row = [&](int level, int pos) {
@@ -809,7 +832,6 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
             emit(FOP_UC, depth, 0, (uint32_t)node);
         } else if (depth == top) {
             if (plain(depth, node)) {
-                while ((stream.size() / 32) % 4) push_pad();
                 emit(FOP_SUB8, depth, 0, (uint32_t)node);
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int Bn = heap(top + 1, 2 * node + (c4 >> 1));
@@ -847,7 +869,24 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         }
     };
     walk(0, 0);
-    if (!ok) return;
+    if (!ok || ops.empty()) return;
+    op_lines.back().swap(stream);
+    // assemble: every 16 ops one "op line" (op k of the batch = words 2k, 2k+1), then each op's own lines; a SUB8
+    // op starts on a chunk boundary.  The ops thus ride the same prefetched stream as the tables they drive.
+    stream.clear();
+    for (size_t i = 0; i < ops.size(); ++i) {
+        if (i % 16 == 0) {
+            uint32_t line[32];
+            for (int k = 0; k < 16; ++k) {
+                const bool have = i + k < ops.size();
+                line[2 * k] = have ? ops[i + k].x : 0xffu;
+                line[2 * k + 1] = have ? ops[i + k].y : 0u;
+            }
+            stream.insert(stream.end(), line, line + 32);
+        }
+        if ((ops[i].x & 0xffu) == FOP_SUB8) while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
+        stream.insert(stream.end(), op_lines[i].begin(), op_lines[i].end());
+    }
     // pad to whole chunks of 4 lines and transpose each chunk to [lane][4]
     while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
     const int n_lines = (int)(stream.size() / 32);
@@ -864,7 +903,7 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     if (P.n_chunks < 1) return;
     std::vector<uint32_t> fw((N + 31) / 32, 0);
     for (int i = 0; i < N; ++i) if (frozen[i] == 1) fw[i >> 5] |= 1u << (i & 31);
-    if (!fast_upload(pl, stream, &P.stream) || !fast_upload(pl, fw, &P.frozen_words) || !fast_upload(pl, ops, &P.ops)) { free_fast_plan(pl); return; }
+    if (!fast_upload(pl, stream, &P.stream) || !fast_upload(pl, fw, &P.frozen_words)) { free_fast_plan(pl); return; }
     if (d.ca) {
         // remainder of the unit message e_k under the reference's long division (utils.cpp:77-93): linear, so the
         // CRC of a word is the XOR of the remainders of its set bits
