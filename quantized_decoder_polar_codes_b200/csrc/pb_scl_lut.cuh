@@ -82,6 +82,28 @@ __device__ __forceinline__ void cp_async_wait() {
 
 __device__ __noinline__ void sort_idx_noinline(int *idx, int n, const double *key) { std_sort_idx(idx, n, key); }
 
+struct RingState {
+    unsigned fetch_off;   // byte offset (within the stream) of the next chunk to prefetch
+    unsigned chunk_no;    // chunks consumed so far
+};
+__device__ __forceinline__ void ring_issue(RingState &rs, unsigned slot, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(ring_lane + slot * 512u), "l"(stream_lane + rs.fetch_off));
+    rs.fetch_off += 512u;
+    if (rs.fetch_off == stream_bytes) rs.fetch_off = 0;
+}
+__device__ __forceinline__ uint4 ring_next_chunk(RingState &rs, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
+    const unsigned slot = rs.chunk_no & (kRingChunks - 1);
+    ring_issue(rs, (slot + kRingChunks - 1) & (kRingChunks - 1), ring_lane, stream_lane, stream_bytes);   // refill the slot consumed before
+    cp_async_wait<kRingChunks - 1>();                                                                     // ... and make sure this chunk has landed
+    ++rs.chunk_no;
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_lane + slot * 512u));
+    return v;
+}
+__device__ __noinline__ uint4 ring_next_chunk_outlined(RingState *rs, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
+    return ring_next_chunk(*rs, ring_lane, stream_lane, stream_bytes);
+}
+
 // 4 symbol bytes -> 4 nibbles (16 bits)
 __device__ __forceinline__ uint32_t pack4(uint32_t x) {
     return (x & 0xfu) | ((x >> 4) & 0xf0u) | ((x >> 8) & 0xf00u) | ((x >> 12) & 0xf000u);
@@ -113,25 +135,15 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     //      is consumed exactly once per pass, in a fixed order, and lane l only ever needs word l of a line.  The
     //      host lays the lines out in consumption order, 4 lines per lane-transposed 512-byte chunk, and each
     //      lane streams ITS 16 bytes of every chunk with cp.async into a private ring (no cross-lane sync). ----
-    unsigned fetch_off = 0;            // byte offset (within the stream) of the next chunk to prefetch
-    unsigned chunk_no = 0;             // chunks consumed so far
+    RingState rs{0u, 0u};
     const unsigned stream_bytes = (unsigned)fp.n_chunks * 512u;
     const char *stream_lane = reinterpret_cast<const char *>(fp.stream) + lane * 16;
     const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(RING + lane * 4);   // this lane's 16 bytes of slot 0
-    auto issue_chunk = [&](unsigned slot) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(ring_lane + slot * 512u), "l"(stream_lane + fetch_off));
-        fetch_off += 512u;
-        if (fetch_off == stream_bytes) fetch_off = 0;
-    };
-    for (int i = 0; i < kRingChunks - 1; ++i) issue_chunk(i);
+    for (int i = 0; i < kRingChunks - 1; ++i) ring_issue(rs, i, ring_lane, stream_lane, stream_bytes);
+    // the Fast-SSC variant has ~40 consumption sites; keeping the refill out of line keeps its code in the I-cache
     auto next_chunk = [&]() -> uint4 {
-        const unsigned slot = chunk_no & (kRingChunks - 1);
-        issue_chunk((slot + kRingChunks - 1) & (kRingChunks - 1));   // refill the slot consumed before this one
-        cp_async_wait<kRingChunks - 1>();                            // ... and make sure this chunk has landed
-        ++chunk_no;
-        uint4 v;
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_lane + slot * 512u));
-        return v;
+        if (FAST) return ring_next_chunk_outlined(&rs, ring_lane, stream_lane, stream_bytes);
+        return ring_next_chunk(rs, ring_lane, stream_lane, stream_bytes);
     };
     // upper-level steps take their 1 or 2 lines one at a time out of the current chunk
     uint4 ucur = make_uint4(0, 0, 0, 0);
