@@ -125,6 +125,21 @@ def test_both_schedule_interpreters(q, kind, ckw, force, kernel, monkeypatch):
     assert bad == 0, f"{bad}/{x.shape[0]} frames differ ({dec.kernel})"
 
 
+import real_lut
+
+
+@pytest.mark.parametrize("tag,kind", real_lut.CASES, ids=[f"{t}-{k}" for t, k in real_lut.CASES])
+def test_cuda_matches_reference_on_real_mindistortion_luts(q, tag, kind):
+    """BASELINE.json configs 2/3 with REAL MinDistortion tables (reference generator code) on AWGN frames
+    quantized with the driver's channel quantizer: bit-exact vs the compiled reference's outputs, and the
+    BLER computed from our decoder equals the reference's (identical decisions => identical curves)."""
+    kw, x, want, msg = real_lut.build_kwargs(real_lut.load(), tag, kind)
+    dec = _build(q, kind, kw)
+    got = dec.decode(x)
+    assert (got == want).all(), dec.kernel
+    assert (got != msg).any(axis=1).mean() == (want != msg).any(axis=1).mean()
+
+
 def test_reference_call_conventions(q):
     """(N,), (1,N), float64 symbols (forcecast like py::array_t<int>), uint8 fast path, batch of one."""
     kw, x, _ = common.make_case("SCLLUTDecoder", N=128, K=32, L=8, B=8, seed=3)

@@ -94,6 +94,21 @@ def test_std_sort_emulation_matches_libstdcpp(real_std_sort, n):
             assert (idx == np.argsort(keys, kind="stable")).all()
 
 
+import real_lut
+
+
+@pytest.mark.parametrize("tag,kind", real_lut.CASES, ids=[f"{t}-{k}" for t, k in real_lut.CASES])
+def test_oracle_matches_reference_on_real_mindistortion_luts(tag, kind):
+    """BASELINE.json configs 2/3: tables from the reference's own MinDistortion generator code (N=128, Q=16,
+    design SNR 3 dB), channel quantizer and frame loop of mainQuantizedDecoder_LLRDomain.py; outputs of the
+    compiled reference decoders are the golden vectors (tests/golden/make_real_luts.py)."""
+    kw, x, want, msg = real_lut.build_kwargs(real_lut.load(), tag, kind)
+    got = po.OracleDecoder(kind, **kw).decode(x.astype(np.int32))
+    assert (got == want).all()
+    if tag.endswith("eb3") and "crc" not in tag:
+        assert (got != msg).any(axis=1).mean() < 0.06   # a working decoder: BLER at 3 dB
+
+
 def test_truthful_decoding_on_clean_channel():
     """Sanity of the whole chain (encoder conventions, frozen mask, CRC): high SNR => message recovered."""
     for kind in ["SCDecoder", "FastSCDecoder", "SCLDecoder", "FastSCLDecoder", "CASCLDecoder"]:
