@@ -131,6 +131,32 @@ int pd_set_debug_outputs(pd_decoder *dec, double *dev_pm, int32_t *dev_winner);
 int pd_count_errors(const uint8_t *dev_decoded, const uint8_t *dev_truth, int64_t B, int32_t len,
                     unsigned long long *dev_counters, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * On-device simulation front-end ("next" row f1 of SURVEY.md 8f): the frame generator of the drivers' loop body
+ * (mainQuantizedDecoder_LLRDomain.py:151-176): random message -> [CRC] -> polar encode (natural order) ->
+ * BPSK + AWGN(sigma) -> llr = 2y/sigma^2 -> channel quantizer (edges + lut, the driver's bisect rule), all on
+ * the GPU (Philox counter RNG: frame i of a run always sees the same noise whatever the batch split / GPU).
+ * Decode with pd_decode_device and count with pd_count_errors afterwards. */
+typedef struct pd_sim pd_sim;
+typedef struct pd_sim_config {
+    int32_t N, K, A;              /* K - A CRC bits are appended when crc_n > 0 (then K == A + crc_n) */
+    int32_t device;
+    const int32_t *frozen_bits;   /* [N] */
+    int32_t crc_n;                /* 0 = no CRC */
+    const int32_t *crc_loc;       /* generator exponents as in the drivers' crc_p */
+    int32_t crc_loc_len;
+    const double *edges;          /* channel quantizer: interval_x, n_edges = M+1 ascending edges; NULL -> emit fp64 LLRs */
+    int32_t n_edges;
+    const uint8_t *chan_lut;      /* [M] compressed symbol of uniform cell i */
+    int32_t q_channel;            /* QChannelCompressed (saturation symbol = q_channel-1) */
+} pd_sim_config;
+int pd_sim_create(const pd_sim_config *cfg, pd_sim **out);
+void pd_sim_destroy(pd_sim *sim);
+/* Generates frames [first_frame, first_frame+B) of the run `seed`: dev_msg [B][A] uint8 message bits,
+ * dev_out [B][N] uint8 symbols (quantizer given) or fp64 LLRs.  Asynchronous on cuda_stream. */
+int pd_sim_generate(pd_sim *sim, double sigma, int64_t B, uint64_t seed, uint64_t first_frame,
+                    uint8_t *dev_msg, void *dev_out, void *cuda_stream);
+
 /* Kernels launched by this library on the calling process so far (bench.py reports it as gpu_launches). */
 int64_t pd_launch_count(void);
 /* Name of the kernel variant pd_decode* uses for this decoder ("generic", "scl_lut_warp", ...). */

@@ -36,6 +36,9 @@ def lib():
         L.pd_host_alloc.argtypes = [C.c_size_t]
         L.pd_host_free.argtypes = [C.c_void_p]
         L.pd_destroy.argtypes = [C.c_void_p]
+        L.pd_sim_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.pd_sim_destroy.argtypes = [C.c_void_p]
+        L.pd_sim_generate.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -67,3 +70,9 @@ def schedule_stats(decoder):
     a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
     check(lib().pd_schedule_stats(decoder._handle, C.byref(a), C.byref(b), C.byref(c)))
     return {"steps": a.value, "elem_ops_per_path": b.value, "sorts": c.value}
+
+
+class SimConfig(C.Structure):
+    _fields_ = [("N", C.c_int32), ("K", C.c_int32), ("A", C.c_int32), ("device", C.c_int32),
+                ("frozen_bits", C.c_void_p), ("crc_n", C.c_int32), ("crc_loc", C.c_void_p), ("crc_loc_len", C.c_int32),
+                ("edges", C.c_void_p), ("n_edges", C.c_int32), ("chan_lut", C.c_void_p), ("q_channel", C.c_int32)]

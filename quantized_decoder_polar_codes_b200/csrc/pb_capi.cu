@@ -21,6 +21,7 @@
 #include "pb_generic.cuh"
 #include "pb_scl_lut.cuh"
 #include "pb_path_warp.cuh"
+#include "pb_sim.cuh"
 
 using namespace pb;
 
@@ -584,6 +585,96 @@ int pd_count_errors(const uint8_t *dev_decoded, const uint8_t *dev_truth, int64_
     int threads = 128;
     int grid = (int)std::min<int64_t>((B + threads - 1) / threads, 148 * 8);
     count_errors_kernel<<<grid, threads, 0, (cudaStream_t)cuda_stream>>>(dev_decoded, dev_truth, B, len, dev_counters);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PD_OK;
+}
+
+// ---- on-device frame generator -------------------------------------------------------------------
+}  // extern "C"
+struct pd_sim {
+    SimDev dev{};
+    int device = 0;
+    std::vector<void *> allocs;
+};
+extern "C" {
+
+void pd_sim_destroy(pd_sim *S) {
+    if (!S) return;
+    cudaSetDevice(S->device);
+    for (void *p : S->allocs) cudaFree(p);
+    delete S;
+}
+
+int pd_sim_create(const pd_sim_config *c, pd_sim **out) {
+    if (!c || !out || !c->frozen_bits) return fail(PD_EINVAL, "null argument");
+    *out = nullptr;
+    const int N = c->N;
+    if (N < 32 || N > (1 << kMaxLog) || (N & (N - 1))) return fail(PD_EINVAL, "N=%d must be a power of two in [32,%d]", N, 1 << kMaxLog);
+    std::vector<int32_t> info_pos;
+    for (int i = 0; i < N; ++i) if (c->frozen_bits[i] == 0) info_pos.push_back(i);
+    if ((int)info_pos.size() != c->K) return fail(PD_EINVAL, "K=%d but frozen_bits has %zu non-frozen positions", c->K, info_pos.size());
+    if (c->crc_n < 0 || c->crc_n > 32) return fail(PD_EINVAL, "crc_n must be in [0,32]");
+    if (c->A < 1 || c->A + c->crc_n != c->K) return fail(PD_EINVAL, "need K == A + crc_n");
+    if (c->edges && (c->n_edges < 2 || !c->chan_lut || c->q_channel < 1 || c->q_channel > 256)) return fail(PD_EINVAL, "bad channel quantizer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PD_ECUDA, "no CUDA device");
+    if (c->device < 0 || c->device >= ndev) return fail(PD_EINVAL, "device %d out of range", c->device);
+    CUDA_TRY(cudaSetDevice(c->device));
+    pd_sim *S = new pd_sim();
+    S->device = c->device;
+    SimDev &d = S->dev;
+    d.N = N; d.K = c->K; d.A = c->A; d.crc_n = c->crc_n;
+    auto up = [&](const void *h, size_t bytes, const void **dst) -> int {
+        void *p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return fail(PD_ECUDA, "cudaMalloc failed");
+        S->allocs.push_back(p);
+        if (bytes && cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return fail(PD_ECUDA, "cudaMemcpy failed");
+        *dst = p;
+        return PD_OK;
+    };
+    int rc;
+    if ((rc = up(info_pos.data(), info_pos.size() * 4, (const void **)&d.info_pos))) { pd_sim_destroy(S); return rc; }
+    std::vector<uint32_t> rem(c->A, 0);
+    if (c->crc_n > 0) {
+        std::vector<int> poly(c->crc_n + 1, 0);
+        for (int i = 0; i < c->crc_loc_len; ++i) {
+            if (c->crc_loc[i] < 0 || c->crc_loc[i] > c->crc_n) { pd_sim_destroy(S); return fail(PD_EINVAL, "crc_p entry out of range"); }
+            poly[c->crc_loc[i]] = 1;
+        }
+        uint32_t taps = 0;
+        for (int k = 0; k < c->crc_n; ++k) if (poly[1 + k]) taps |= 1u << (c->crc_n - 1 - k);
+        const uint32_t msb = 1u << (c->crc_n - 1), mask = c->crc_n >= 32 ? 0xffffffffu : ((1u << c->crc_n) - 1u);
+        for (int k = 0; k < c->A; ++k) {
+            uint32_t reg = 0;
+            for (int i = k; i < c->A; ++i) {
+                uint32_t top = ((reg & msb) ? 1u : 0u) ^ (i == k ? 1u : 0u);
+                reg = (reg << 1) & mask;
+                if (top) reg ^= taps;
+            }
+            rem[k] = reg;
+        }
+    }
+    if ((rc = up(rem.data(), rem.size() * 4, (const void **)&d.crc_rem))) { pd_sim_destroy(S); return rc; }
+    if (c->edges) {
+        if ((rc = up(c->edges, (size_t)c->n_edges * 8, (const void **)&d.edges)) ||
+            (rc = up(c->chan_lut, (size_t)(c->n_edges - 1), (const void **)&d.chan_lut))) { pd_sim_destroy(S); return rc; }
+        d.n_edges = c->n_edges;
+        d.q_channel = c->q_channel;
+    }
+    *out = S;
+    return PD_OK;
+}
+
+int pd_sim_generate(pd_sim *S, double sigma, int64_t B, uint64_t seed, uint64_t first_frame, uint8_t *dev_msg, void *dev_out, void *cuda_stream) {
+    if (!S || (B > 0 && (!dev_msg || !dev_out))) return fail(PD_EINVAL, "null argument");
+    if (!(sigma > 0)) return fail(PD_EINVAL, "sigma must be > 0");
+    if (B <= 0) return PD_OK;
+    CUDA_TRY(cudaSetDevice(S->device));
+    const int threads = 128, wpb = threads / 32;
+    const size_t smem = (size_t)wpb * (S->dev.N / 32) * 4;
+    const int grid = (int)std::min<int64_t>((B + wpb - 1) / wpb, 148 * 16);
+    sim_generate_kernel<<<grid, threads, smem, (cudaStream_t)cuda_stream>>>(S->dev, sigma, B, seed, first_frame, dev_msg, dev_out);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return PD_OK;

@@ -109,6 +109,8 @@ def main():
             x = quantize(sim.awgn_llr(sim.polar_encode(word, fm), sigma, rng), ix, clut)
             tag = f"A{A}{'crc' if crc else ''}_eb{eb:.0f}"
             out[tag + "/x"] = x.astype(np.uint8)
+            out[tag + "/chan_edges"] = np.asarray(ix, np.float64)
+            out[tag + "/chan_lut"] = np.asarray(clut, np.uint8)
             out[tag + "/msg"] = msg
             for kind in kinds:
                 kw = dict(N=N, K=K, frozen_bits=fm, message_bits=mm, virtual_channel_llr=llr_quanta)
