@@ -50,7 +50,7 @@ struct PathPlan {
 };
 
 template <int DOM, int LOGL>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 20)
 path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathParams pp, const void *__restrict__ in, int in_dtype,
                  uint8_t *__restrict__ out, long long B, char *__restrict__ ws, int *err_flag, double *dbg_pm, int *dbg_win) {
     using T = typename Val<DOM>::T;
