@@ -103,6 +103,20 @@ __device__ __forceinline__ uint4 ring_next_chunk(RingState &rs, unsigned ring_la
 __device__ __noinline__ uint4 ring_next_chunk_outlined(RingState *rs, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
     return ring_next_chunk(*rs, ring_lane, stream_lane, stream_bytes);
 }
+struct LineState {
+    RingState rs;
+    uint4 cur;   // the chunk lines are currently taken from
+    int q;       // next line inside `cur` (4 = exhausted)
+};
+__device__ __forceinline__ uint32_t next_line_inl(LineState &ls, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
+    if (ls.q == 4) { ls.cur = ring_next_chunk(ls.rs, ring_lane, stream_lane, stream_bytes); ls.q = 0; }
+    const uint32_t v = ls.q == 0 ? ls.cur.x : ls.q == 1 ? ls.cur.y : ls.q == 2 ? ls.cur.z : ls.cur.w;
+    ++ls.q;
+    return v;
+}
+__device__ __noinline__ uint32_t next_line_outlined(LineState *ls, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
+    return next_line_inl(*ls, ring_lane, stream_lane, stream_bytes);
+}
 
 // 4 symbol bytes -> 4 nibbles (16 bits)
 __device__ __forceinline__ uint32_t pack4(uint32_t x) {
@@ -135,24 +149,22 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     //      is consumed exactly once per pass, in a fixed order, and lane l only ever needs word l of a line.  The
     //      host lays the lines out in consumption order, 4 lines per lane-transposed 512-byte chunk, and each
     //      lane streams ITS 16 bytes of every chunk with cp.async into a private ring (no cross-lane sync). ----
-    RingState rs{0u, 0u};
+    LineState ls;
+    ls.rs.fetch_off = 0u; ls.rs.chunk_no = 0u; ls.cur = make_uint4(0, 0, 0, 0); ls.q = 4;
     const unsigned stream_bytes = (unsigned)fp.n_chunks * 512u;
     const char *stream_lane = reinterpret_cast<const char *>(fp.stream) + lane * 16;
     const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(RING + lane * 4);   // this lane's 16 bytes of slot 0
-    for (int i = 0; i < kRingChunks - 1; ++i) ring_issue(rs, i, ring_lane, stream_lane, stream_bytes);
-    // the Fast-SSC variant has ~40 consumption sites; keeping the refill out of line keeps its code in the I-cache
+    for (int i = 0; i < kRingChunks - 1; ++i) ring_issue(ls.rs, i, ring_lane, stream_lane, stream_bytes);
+    // the Fast-SSC variant has ~40 consumption sites: there the stream accessors are real (out-of-line) functions so
+    // that the hot code stays inside the instruction cache; the plain variant inlines them
     auto next_chunk = [&]() -> uint4 {
-        if (FAST) return ring_next_chunk_outlined(&rs, ring_lane, stream_lane, stream_bytes);
-        return ring_next_chunk(rs, ring_lane, stream_lane, stream_bytes);
+        if (FAST) return ring_next_chunk_outlined(&ls.rs, ring_lane, stream_lane, stream_bytes);
+        return ring_next_chunk(ls.rs, ring_lane, stream_lane, stream_bytes);
     };
-    // upper-level steps take their 1 or 2 lines one at a time out of the current chunk
-    uint4 ucur = make_uint4(0, 0, 0, 0);
-    int uq = 4;
+    // upper-level steps and special nodes take their lines one at a time out of the current chunk
     auto next_line = [&]() -> uint32_t {
-        if (uq == 4) { ucur = next_chunk(); uq = 0; }
-        const uint32_t v = uq == 0 ? ucur.x : uq == 1 ? ucur.y : uq == 2 ? ucur.z : ucur.w;
-        ++uq;
-        return v;
+        if (FAST) return next_line_outlined(&ls, ring_lane, stream_lane, stream_bytes);
+        return next_line_inl(ls, ring_lane, stream_lane, stream_bytes);
     };
     // eight f (or g) lookups for one word of symbols: out nibble k = T[u_k][a_k][b_k] with a_k / b_k nibble k of A / Bv.
     // Even and odd nibbles are split into byte lanes so that shuffle sources (a*2 + b>>3) and nibble shifts ((b&7)*4)
@@ -216,6 +228,15 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             return pack4(x0) | (pack4(x1) << 16);
         };
 
+        // level 0: the frame's channel symbols, range-checked and packed 8 per word ONCE, into the group's slot-0 column
+        // of the workspace (every path of the frame reads the same column; the root f and g steps then look like any
+        // other level).  Lane `me` packs words me, me+L, ...
+        {
+            uint32_t *g0 = G + (size_t)fp.voff[0] * 32 + gbase;
+            for (int w = me; w < (N >> 3); w += L) g0[w * 32] = in8(8 * w);
+            __syncwarp();
+        }
+
         double PM = (me == 0) ? 0.0 : d.pm_init;
         // 3-bit-per-level slot pointers for levels 1..top: values (pv) and left-child partial sums (pu)
         uint32_t pv = 0x09249249u * (uint32_t)me, pu = pv;
@@ -234,13 +255,13 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             const uint32_t t0 = next_line();
             uint32_t t1 = t0;
             if (isg) t1 = next_line();
-            const uint32_t *src = (dd == 0) ? nullptr : level_ptr(dd, vslot(dd));
+            const uint32_t *src = (dd == 0) ? G + (size_t)fp.voff[0] * 32 + gbase : level_ptr(dd, vslot(dd));
             uint32_t *dst = level_ptr(dd + 1, lane);
             const uint32_t *xsrc = X + uslot(dd + 1);
             const uint32_t ub0 = (2u * node) * (uint32_t)ct;
             const int nw = ct >> 3;
-            auto getA = [&](int w) -> uint32_t { return dd == 0 ? in8(8 * w) : src[w * 32]; };
-            auto getB = [&](int w) -> uint32_t { return dd == 0 ? in8(N / 2 + 8 * w) : src[(nw + w) * 32]; };
+            auto getA = [&](int w) -> uint32_t { return src[w * 32]; };
+            auto getB = [&](int w) -> uint32_t { return src[(nw + w) * 32]; };
             auto getU = [&](int w) -> uint32_t {
                 if (!isg) return 0u;
                 const uint32_t bit = ub0 + 8u * w;
@@ -555,7 +576,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 const bool whole = !FAST || ot == FOP_SUB8;
                 const int s = whole ? (int)onode : (int)(onode >> 2);
                 const uint32_t fz = (__ldg(fp.frozen_words + (s >> 2)) >> ((s & 3) * 8)) & 0xffu;
-                if (whole) { uq = 4; w3 = *level_ptr(top, vslot(top)); xb = 0; }
+                if (whole) { ls.q = 4; w3 = *level_ptr(top, vslot(top)); xb = 0; }
                 const int c4_end = whole ? 4 : (int)(onode & 3u) + 1;
 #pragma unroll 1
                 for (int c4 = whole ? 0 : (int)(onode & 3u); c4 < c4_end; ++c4) {
@@ -939,7 +960,8 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     // global workspace -- they are touched only a handful of times per frame and stay L2-resident --, the small,
     // hot ones stay in shared memory.  This is what sets the occupancy (warps per SM).
     const int FPW = 32 / L;
-    int gl = 0, goff = 0, soff = 0;
+    int gl = 0, goff = N / 8, soff = 0;   // workspace starts with the packed level-0 (channel) words
+    P.voff[0] = 0;
     for (int lev = 1; lev <= n - 3; ++lev) {
         int words = (N >> lev) / 8;
         if (words > 8) { P.voff[lev] = goff; goff += words; gl = lev; }
