@@ -28,22 +28,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N, K, L, Q = 1024, 512, 8, 16
-EBN0_DB = 3.0
-WORKLOAD = "SCL-LUT N=1024 A=K=512 L=8 QDecoder=QChannel=16 (uniform-grid min-sum LUTs), AWGN Eb/N0=3.0 dB, NR-sequence frozen set"
+EBN0_DB = 2.0
+WORKLOAD = "SCL-LUT N=1024 A=K=512 L=8 QDecoder=QChannel=16, MinDistortion LUTs (reference generator, design 3 dB), AWGN Eb/N0=2.0 dB through the driver's channel quantizer, NR-sequence frozen set"
 METRIC = "decoded frames/s (info Gbit/s = frames/s*512/1e9), N=1024 L=8 SCL-LUT"
 BYTES_PER_FRAME = N + K  # uint8 symbols in + uint8 bits out
 
 
 def make_workload(frames, seed):
+    """Real MinDistortion tables for N=1024, Q=16, design SNR 3 dB, produced by the reference's own generator code
+    (tests/golden/make_real_lut_n1024.py), the channel quantizer the reference driver builds at this Eb/N0
+    (mainQuantizedDecoder_LLRDomain.py:130-145) and its per-symbol rule (:167-176), vectorised."""
     from quantized_decoder_polar_codes_b200 import simulation as sim
     rng = np.random.default_rng(seed)
+    z = np.load(os.path.join(ROOT, "quantized_decoder_polar_codes_b200", "data", "mindistortion_n1024_q16_3dB.npz"))
     fm, mm = sim.frozen_mask(N, K)
-    f, g, llr = sim.minsum_lut_tables(N, Q, per_position=False)
+    f = [z["lut_f"][p].astype(np.int32)[None] for p in range(N - 1)]
+    g = [z["lut_g"][p].astype(np.int32)[None] for p in range(N - 1)]
+    llr_tab = z["llr_quanta"]
+    edges, clut = z[f"chan_A{K}_eb{EBN0_DB:.0f}/edges"], z[f"chan_A{K}_eb{EBN0_DB:.0f}/lut"]
     msg = rng.integers(0, 2, (frames, K), dtype=np.uint8)
     cw = sim.polar_encode(msg, fm)
-    sigma = sim.awgn_sigma(EBN0_DB, K / N)
-    sym = sim.quantize_uniform(sim.awgn_llr(cw, sigma, rng), Q, 1.0).astype(np.uint8)
-    kw = dict(N=N, K=K, L=L, frozen_bits=fm, message_bits=mm, LUT_f=f, LUT_g=g, virtual_channel_llr=llr)
+    llr = sim.awgn_llr(cw, sim.awgn_sigma(EBN0_DB, K / N), rng)
+    idx = np.clip(np.searchsorted(edges[:-1], llr, side="left") - 1, 0, clut.size - 1)
+    sym = np.where(llr <= edges[0], 0, np.where(llr >= edges[-1], Q - 1, clut[idx])).astype(np.uint8)
+    kw = dict(N=N, K=K, L=L, frozen_bits=fm, message_bits=mm, LUT_f=f, LUT_g=g, virtual_channel_llr=llr_tab)
     return kw, sym, msg
 
 

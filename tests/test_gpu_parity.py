@@ -140,6 +140,20 @@ def test_cuda_matches_reference_on_real_mindistortion_luts(q, tag, kind):
     assert (got != msg).any(axis=1).mean() == (want != msg).any(axis=1).mean()
 
 
+def test_north_star_workload_of_the_benchmark(q):
+    """Exactly what bench.py decodes: SCL-LUT N=1024 A=512 L=8 with the REAL MinDistortion tables (reference
+    generator code) and the driver's channel quantizer at 2 dB -- bit-exact vs the oracle (which equals the compiled
+    reference on these tables, tests/test_oracle.py), and a sane BLER."""
+    import bench
+    kw, sym, msg = bench.make_workload(600, seed=3)
+    dec = q.SCLLUTDecoder(**kw)
+    assert dec.kernel == "scl_lut_warp"
+    got = dec.decode(sym)
+    want = po.OracleDecoder("SCLLUTDecoder", **kw).decode(sym.astype(np.int32))
+    assert (got == want).all()
+    assert (got != msg).any(axis=1).mean() < 0.2
+
+
 def test_reference_call_conventions(q):
     """(N,), (1,N), float64 symbols (forcecast like py::array_t<int>), uint8 fast path, batch of one."""
     kw, x, _ = common.make_case("SCLLUTDecoder", N=128, K=32, L=8, B=8, seed=3)

@@ -109,6 +109,15 @@ def test_oracle_matches_reference_on_real_mindistortion_luts(tag, kind):
         assert (got != msg).any(axis=1).mean() < 0.06   # a working decoder: BLER at 3 dB
 
 
+def test_oracle_matches_compiled_reference_on_benchmark_workload(refmod):
+    """The benchmark's real N=1024 MinDistortion tables: many duplicated / zero LLR quanta, i.e. constant ties."""
+    import bench
+    kw, sym, msg = bench.make_workload(12, seed=4)
+    want = common.ref_decode(refmod, "SCLLUTDecoder", kw, sym.astype(np.int32))
+    got = po.OracleDecoder("SCLLUTDecoder", **kw).decode(sym.astype(np.int32))
+    assert (got == want).all()
+
+
 def test_truthful_decoding_on_clean_channel():
     """Sanity of the whole chain (encoder conventions, frozen mask, CRC): high SNR => message recovered."""
     for kind in ["SCDecoder", "FastSCDecoder", "SCLDecoder", "FastSCLDecoder", "CASCLDecoder"]:
