@@ -224,13 +224,19 @@ def run_ours(args, rank, local_rank, world):
     d_in = torch.from_numpy(sym).to(dev)
     d_truth = torch.from_numpy(msg).to(dev)
     d_out = torch.empty((F, K), dtype=torch.uint8, device=dev)
-    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)   # run totals (identical on every rank)
+    step_cnt = torch.zeros(2, dtype=torch.int64, device=dev)   # this step's local counts -> all-reduced -> added to the totals
     assert d_in.numel() >= 126 * 2 ** 20 or args.batch < 131072, "inputs must exceed L2"
+
+    def count_and_reduce():
+        step_cnt.zero_()
+        capi.check(lib.pd_count_errors(d_out.data_ptr(), d_truth.data_ptr(), F, K, step_cnt.data_ptr(), stream))
+        D.allreduce_counters(step_cnt)   # the path's only exchange: 2 x int64 over NCCL/NVLink
+        counters.add_(step_cnt)
 
     def step_device():
         capi.decode_device(dec, d_in.data_ptr(), capi.PD_U8, F, d_out.data_ptr(), stream)
-        capi.check(lib.pd_count_errors(d_out.data_ptr(), d_truth.data_ptr(), F, K, counters.data_ptr(), stream))
-        D.allreduce_counters(counters)   # the path's only exchange: 2 x int64 over NCCL/NVLink
+        count_and_reduce()
 
     def barrier():
         D.barrier()
@@ -253,8 +259,7 @@ def run_ours(args, rank, local_rank, world):
             kev[i][0].record()
             capi.decode_device(dec, d_in.data_ptr(), capi.PD_U8, F, d_out.data_ptr(), stream)
             kev[i][1].record()
-            capi.check(lib.pd_count_errors(d_out.data_ptr(), d_truth.data_ptr(), F, K, counters.data_ptr(), stream))
-            D.allreduce_counters(counters)
+            count_and_reduce()
         ev[1].record()
         barrier()
         l_after = lib.pd_launch_count()
@@ -265,7 +270,7 @@ def run_ours(args, rank, local_rank, world):
     kernel_ms = D.max_over_ranks(kernel_ms, dev)
     value = world * F * args.steps / (elapsed_ms / 1e3)
     cnt = counters.cpu().tolist()
-    total_frames = world * F * args.steps if world > 1 else F * args.steps
+    total_frames = world * F * args.steps
 
     # --- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside) ---
     h_in_p = lib.pd_host_alloc(F * N)
