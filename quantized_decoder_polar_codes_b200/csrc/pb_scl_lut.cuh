@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <type_traits>
@@ -29,6 +31,10 @@
 
 #include "pb_generic.cuh"
 #include "pb_internal.h"
+
+#ifndef PB_EXP_LINE
+#define PB_EXP_LINE 0
+#endif
 
 namespace pb {
 
@@ -158,12 +164,12 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     // the Fast-SSC variant has ~40 consumption sites: there the stream accessors are real (out-of-line) functions so
     // that the hot code stays inside the instruction cache; the plain variant inlines them
     auto next_chunk = [&]() -> uint4 {
-        if (FAST) return ring_next_chunk_outlined(&ls.rs, ring_lane, stream_lane, stream_bytes);
+        if (FAST && L > 1) return ring_next_chunk_outlined(&ls.rs, ring_lane, stream_lane, stream_bytes);
         return ring_next_chunk(ls.rs, ring_lane, stream_lane, stream_bytes);
     };
     // upper-level steps and special nodes take their lines one at a time out of the current chunk
     auto next_line = [&]() -> uint32_t {
-        if (FAST) return next_line_outlined(&ls, ring_lane, stream_lane, stream_bytes);
+        if (FAST && L > 1) return next_line_outlined(&ls, ring_lane, stream_lane, stream_bytes);
         return next_line_inl(ls, ring_lane, stream_lane, stream_bytes);
     };
     // eight f (or g) lookups for one word of symbols: out nibble k = T[u_k][a_k][b_k] with a_k / b_k nibble k of A / Bv.
@@ -394,6 +400,16 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         // virtual_channel_llrs[dd-1][pos][symbol] (PD/src/FastSCLLUTDecoder.cpp:89,112,179), one stream line per element
         auto special = [&](int spt, int dd, uint32_t node) {
             const int temp = N >> dd;
+            // the node's LLR lines start on a chunk boundary: four elements per chunk, no per-line bookkeeping
+            if (!(L == 1 && spt == 0)) ls.q = 4;   // (the non-list R0 reads no LLRs and has no lines)
+            uint4 ech = make_uint4(0, 0, 0, 0);
+            auto elem_line = [&](int j) -> uint32_t {
+                if (PB_EXP_LINE) return next_line();
+                if ((j & 3) == 0) ech = next_chunk();
+                return (j & 3) == 0 ? ech.x : (j & 3) == 1 ? ech.y : (j & 3) == 2 ? ech.z : ech.w;
+            };
+            // a node of 2 elements leaves half a chunk: the following ops' lines continue there
+            auto elem_done = [&]() { if (!PB_EXP_LINE && (temp & 3)) { ls.cur = ech; ls.q = temp & 3; } };
             const uint32_t full = temp >= 32 ? 0xffffffffu : ((1u << temp) - 1u);
             if (L == 1) {
                 // PD/src/FastSCLUT.cpp:43-106
@@ -407,7 +423,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 uint32_t bits = 0, sw = 0;
                 for (int j = 0; j < temp; ++j) {
                     if ((j & 7) == 0) sw = node_word(dd, j >> 3);
-                    const double DM = llr_of(next_line(), nib(sw, j & 7));
+                    const double DM = llr_of(elem_line(j), nib(sw, j & 7));
                     const uint32_t hd = DM <= 0 ? 1u : 0u;
                     S += DM;
                     parity ^= (int)hd;
@@ -418,6 +434,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                         bits = 0;
                     }
                 }
+                elem_done();
                 if (temp <= 32) {
                     if (spt == 2) bits = (S <= 0) ? full : 0u;   // REP
                     if (spt == 3 && parity) bits ^= 1u << amin;  // SPC: Wagner flip
@@ -442,7 +459,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 uint32_t sw = 0;
                 for (int j = 0; j < temp; ++j) {
                     if ((j & 7) == 0) sw = node_word(dd, j >> 3);
-                    const double l = llr_of(next_line(), nib(sw, j & 7));
+                    const double l = llr_of(elem_line(j), nib(sw, j & 7));
                     const double al = fabs(l);
                     if (spt == 0) {
                         PM += (double)(float)(l < 0) * al;
@@ -456,6 +473,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                     }
                 }
             }
+            elem_done();
             if (spt == 0) rounds = 0;
             if (spt == 1) {
                 // argsort(abs_llr) in libstdc++'s order; only its first min(L-1,temp) entries are ever used
@@ -510,6 +528,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         };
 
         // ---- the compiled tree walk ----
+        ls.q = 4;           // every pass starts on a fresh chunk (the stream is padded to a chunk boundary at its end)
         uint32_t opl = 0;   // this lane's word of the current op line (16 ops)
         for (int oi = 0; oi < fp.n_ops; ++oi) {
             if ((oi & 15) == 0) opl = next_line();
@@ -917,7 +936,9 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
             }
             stream.insert(stream.end(), line, line + 32);
         }
-        if ((ops[i].x & 0xffu) == FOP_SUB8) while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
+        const uint32_t oty = ops[i].x & 0xffu;
+        if (oty == FOP_SUB8 || (oty == FOP_SP && !op_lines[i].empty()))
+            while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
         stream.insert(stream.end(), op_lines[i].begin(), op_lines[i].end());
     }
     // pad to whole chunks of 4 lines and transpose each chunk to [lane][4]
@@ -973,6 +994,13 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     P.xwords = N / 32;
     P.scrwords = (L == 1) ? 0 : (N / 32) * FPW;
     P.n_ops = (int)ops.size();
+    if (getenv("POLAR_B200_DEBUG")) {
+        int hist[16] = {0};
+        for (auto &o : ops) hist[o.x & 15u]++;
+        fprintf(stderr, "[polar_b200] fast plan: L=%d n_ops=%d chunks=%d fastk=%d max_special=%d hist:", L, (int)ops.size(), n_lines / 4, (int)(max_special >= 0), max_special);
+        for (int i = 0; i < 14; ++i) fprintf(stderr, " %d", hist[i]);
+        fprintf(stderr, "\n");
+    }
     P.r1_words = has_r1 ? 7 * 32 * 3 : 0;
     size_t words = (size_t)P.vwords * 32 + (size_t)P.xwords * 32 + (size_t)P.scrwords + kRingChunks * 128 + 128 + 32 + P.r1_words;
     pl->smem = words * 4;

@@ -140,6 +140,25 @@ def test_cuda_matches_reference_on_real_mindistortion_luts(q, tag, kind):
     assert (got != msg).any(axis=1).mean() == (want != msg).any(axis=1).mean()
 
 
+@pytest.mark.parametrize("kind,ckw", [
+    ("FastSCLUTDecoder", dict(N=128, K=64, B=400000)),
+    ("SCLUTDecoder", dict(N=128, K=64, B=400000)),
+    ("FastSCLLUTDecoder", dict(N=128, K=64, L=8, B=60000)),
+    ("CAFastSCLLUTDecoder", dict(N=128, K=64, A=40, L=4, B=60000)),
+    ("SCLLUTDecoder", dict(N=128, K=64, L=2, B=120000)),
+], ids=lambda v: v if isinstance(v, str) else f"B{v['B']}")
+def test_persistent_ctas_run_several_passes(q, kind, ckw):
+    """Batches large enough that every (persistent, one-warp) CTA decodes several frame groups back to back: the
+    table/op stream must wrap exactly at the pass boundary (a Fast-SSC walk can end in the middle of a chunk)."""
+    kw, x, _ = common.make_case(kind, seed=80, tables="minsum", ebn0_db=1.0, **ckw)
+    dec = _build(q, kind, kw)
+    assert dec.kernel == "scl_lut_warp"
+    got = dec.decode(x.astype(np.uint8))
+    want = po.OracleDecoder(kind, **kw).decode(x)
+    bad = int((got != want).any(axis=1).sum())
+    assert bad == 0, f"{bad}/{x.shape[0]} frames differ"
+
+
 def test_north_star_workload_of_the_benchmark(q):
     """Exactly what bench.py decodes: SCL-LUT N=1024 A=512 L=8 with the REAL MinDistortion tables (reference
     generator code) and the driver's channel quantizer at 2 dB -- bit-exact vs the oracle (which equals the compiled
