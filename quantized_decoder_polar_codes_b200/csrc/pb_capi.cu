@@ -86,6 +86,8 @@ struct pd_decoder {
     // specialised kernel
     FastPlan fast{};
     PathPlan path{};          // warp-level schedule interpreter (all classes, L power of two)
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};   // pd_decode_device: split of large batches
+    cudaStream_t side[2] = {nullptr, nullptr};
     int force = 0;            // POLAR_B200_FORCE_GENERIC: 1 = CTA-per-frame generic kernel, 2 = path_warp
     const char *kernel_name = "generic";
     int *d_err = nullptr;
@@ -335,6 +337,13 @@ size_t ws_need(const pd_decoder *D, int dtype, const void *d_in, int64_t B) {
     return D->use_smem ? 0 : D->ws_bytes * (size_t)generic_grid(D, B);
 }
 
+// frames one full wave of the chosen (persistent) kernel holds in flight; 0 for the CTA-per-frame generic kernel
+int64_t wave_frames(const pd_decoder *D, int dtype, const void *d_in) {
+    if (want_fast(D, dtype, d_in)) return (int64_t)D->sm_count * D->fast.ctas_per_sm * (32 >> D->fast.logL);
+    if (want_path(D, dtype, d_in)) return (int64_t)D->sm_count * D->path.ctas_per_sm * (32 >> D->path.logL);
+    return 0;
+}
+
 size_t dtype_size(int t) { return t == PD_U8 ? 1 : t == PD_I32 ? 4 : 8; }
 
 int check_dtype(const pd_decoder *D, int t) {
@@ -362,6 +371,8 @@ void pd_destroy(pd_decoder *D) {
         cudaFree(sl.d_in); cudaFree(sl.d_out); cudaFree(sl.ws);
     }
     cudaFree(D->ws_user);
+    for (int i = 0; i < 2; ++i) { if (D->side[i]) { cudaStreamSynchronize(D->side[i]); cudaStreamDestroy(D->side[i]); } if (D->join_ev[i]) cudaEventDestroy(D->join_ev[i]); }
+    if (D->fork_ev) cudaEventDestroy(D->fork_ev);
     for (void *p : D->allocs) cudaFree(p);
     free_fast_plan(&D->fast);
     delete D;
@@ -469,7 +480,6 @@ int pd_create(const pd_config *c, pd_decoder **out) {
     plan_path_warp(D->dev, &D->path);
     if (const char *e = getenv("POLAR_B200_FORCE_GENERIC")) D->force = atoi(e);
     D->kernel_name = (D->fast.ok && D->force == 0) ? D->fast.name : (D->path.ok && D->force != 1) ? "path_warp" : "generic";
-    // frames per pipeline chunk of pd_decode: ~32 MB of input per chunk
     size_t in_frame = (size_t)N * (d.domain == DOM_LUT ? 4 : 8);
     D->chunk_frames = std::max<int64_t>(1024, (int64_t)((32u << 20) / in_frame));
     *out = D;
@@ -499,20 +509,51 @@ int pd_decode_device(pd_decoder *D, const void *dev_in, int in_dtype, int64_t B,
     if (!D || (B > 0 && (!dev_in || !dev_out))) return fail(PD_EINVAL, "null argument");
     int rc = check_dtype(D, in_dtype);
     if (rc) return rc;
+    if (B <= 0) return PD_OK;
     CUDA_TRY(cudaSetDevice(D->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    char *ws = nullptr;
-    if (size_t need = ws_need(D, in_dtype, dev_in, B)) {
-        if (need > D->ws_user_cap) {
-            CUDA_TRY(cudaDeviceSynchronize());
-            cudaFree(D->ws_user);
-            D->ws_user = nullptr; D->ws_user_cap = 0;
-            CUDA_TRY(cudaMalloc((void **)&D->ws_user, need));
-            D->ws_user_cap = need;
-        }
-        ws = D->ws_user;
+    // The decode kernels are persistent (every CTA walks several frame groups), so a single launch ends with a tail
+    // in which most SMs idle.  A large batch is therefore cut into kSplit pieces issued alternately on two internal
+    // streams forked from / joined to the caller's stream with events: the tail of one piece overlaps the next.
+    const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
+    const int64_t wave = wave_frames(D, in_dtype, dev_in);
+    constexpr int kSplit = 4;
+    const bool split = wave > 0 && B >= 8 * wave && ((N * esz) % 16 == 0);
+    const int pieces = split ? kSplit : 1;
+    const int64_t per = split ? (((B + kSplit - 1) / kSplit + 31) & ~(int64_t)31) : B;
+    // workspace: one region per concurrently running piece
+    const size_t need1 = ws_need(D, in_dtype, dev_in, per);
+    const size_t need = need1 * (split ? 2 : 1);
+    if (need > D->ws_user_cap) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(D->ws_user);
+        D->ws_user = nullptr; D->ws_user_cap = 0;
+        CUDA_TRY(cudaMalloc((void **)&D->ws_user, need));
+        D->ws_user_cap = need;
     }
-    return launch(D, dev_in, in_dtype, B, dev_out, s, ws);
+    if (!split) return launch(D, dev_in, in_dtype, B, dev_out, s, D->ws_user);
+    if (!D->fork_ev) {
+        CUDA_TRY(cudaEventCreateWithFlags(&D->fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&D->join_ev[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaStreamCreateWithFlags(&D->side[i], cudaStreamNonBlocking));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(D->fork_ev, s));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamWaitEvent(D->side[i], D->fork_ev, 0));
+    for (int pc = 0; pc < pieces; ++pc) {
+        const int64_t f0 = (int64_t)pc * per, nb = std::min<int64_t>(per, B - f0);
+        if (nb <= 0) break;
+        const int w = pc & 1;
+        if ((rc = launch(D, (const char *)dev_in + (size_t)f0 * N * esz, in_dtype, nb, dev_out + (size_t)f0 * Ko, D->side[w],
+                         D->ws_user ? D->ws_user + (size_t)w * need1 : nullptr)))
+            return rc;
+    }
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventRecord(D->join_ev[i], D->side[i]));
+        CUDA_TRY(cudaStreamWaitEvent(s, D->join_ev[i], 0));
+    }
+    return PD_OK;
 }
 
 int pd_check(pd_decoder *D, void *cuda_stream) {
@@ -535,7 +576,9 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
     if (B <= 0) return PD_OK;
     CUDA_TRY(cudaSetDevice(D->device));
     const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
-    const int64_t chunk = std::min<int64_t>(B, D->chunk_frames);
+    // pipeline chunk: ~16 MB of input (two streams alternate, so copies of one chunk hide behind the kernel of the other
+    // and the tail of one persistent launch overlaps the head of the next)
+    const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(8192, (int64_t)((16u << 20) / (N * esz))));
     for (auto &sl : D->slot) {
         if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         size_t in_need = (size_t)chunk * N * esz, out_need = (size_t)chunk * Ko;
