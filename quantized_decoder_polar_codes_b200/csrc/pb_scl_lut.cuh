@@ -217,11 +217,11 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             uint32_t x0, x1;
             bool bad = false;
             if (in_dtype == 0) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(in) + (size_t)my_frame * N + sym0));
+                const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(in) + (size_t)my_frame * N + sym0));   // streamed: keep L2 for the workspace
                 x0 = v.x; x1 = v.y;
             } else {
                 const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const int32_t *>(in) + (size_t)my_frame * N + sym0);
-                const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+                const uint4 v0 = __ldcs(p), v1 = __ldcs(p + 1);
                 bad = ((v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) & 0xffffff00u) != 0;
                 x0 = (v0.x & 0xff) | ((v0.y & 0xff) << 8) | ((v0.z & 0xff) << 16) | ((v0.w & 0xff) << 24);
                 x1 = (v1.x & 0xff) | ((v1.y & 0xff) << 8) | ((v1.z & 0xff) << 16) | ((v1.w & 0xff) << 24);
@@ -235,11 +235,11 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         };
 
         // level 0: the frame's channel symbols, range-checked and packed 8 per word ONCE, into the group's slot-0 column
-        // of the workspace (every path of the frame reads the same column; the root f and g steps then look like any
+        // of the workspace (every path of the frame reads the same words; the root f and g steps then look like any
         // other level).  Lane `me` packs words me, me+L, ...
         {
-            uint32_t *g0 = G + (size_t)fp.voff[0] * 32 + gbase;
-            for (int w = me; w < (N >> 3); w += L) g0[w * 32] = in8(8 * w);
+            uint32_t *g0 = G + grp;                       // level 0 is stored compactly: [word][frame in warp]
+            for (int w = me; w < (N >> 3); w += L) g0[w * FPW] = in8(8 * w);
             __syncwarp();
         }
 
@@ -261,13 +261,14 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             const uint32_t t0 = next_line();
             uint32_t t1 = t0;
             if (isg) t1 = next_line();
-            const uint32_t *src = (dd == 0) ? G + (size_t)fp.voff[0] * 32 + gbase : level_ptr(dd, vslot(dd));
+            const uint32_t *src = (dd == 0) ? G + grp : level_ptr(dd, vslot(dd));
+            const int sstride = (dd == 0) ? FPW : 32;
             uint32_t *dst = level_ptr(dd + 1, lane);
             const uint32_t *xsrc = X + uslot(dd + 1);
             const uint32_t ub0 = (2u * node) * (uint32_t)ct;
             const int nw = ct >> 3;
-            auto getA = [&](int w) -> uint32_t { return src[w * 32]; };
-            auto getB = [&](int w) -> uint32_t { return src[(nw + w) * 32]; };
+            auto getA = [&](int w) -> uint32_t { return src[w * sstride]; };
+            auto getB = [&](int w) -> uint32_t { return src[(nw + w) * sstride]; };
             auto getU = [&](int w) -> uint32_t {
                 if (!isg) return 0u;
                 const uint32_t bit = ub0 + 8u * w;
@@ -749,7 +750,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             long long frame = g * FPW + grp;
             if (frame < B) {
                 uint8_t *o = out + (size_t)frame * d.Kout;
-                for (int k = me; k < d.Kout; k += L) o[k] = (uint8_t)ubit(d.info_pos[k]);
+                for (int k = me; k < d.Kout; k += L) __stcs(o + k, (uint8_t)ubit(d.info_pos[k]));
                 if (dbg_pm && L > 1) dbg_pm[(size_t)frame * L + me] = PM;
                 if (dbg_pm && L == 1) dbg_pm[frame] = 0.0;
                 if (dbg_win && me == 0) dbg_win[frame] = winner - gbase;
@@ -981,7 +982,8 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     // global workspace -- they are touched only a handful of times per frame and stay L2-resident --, the small,
     // hot ones stay in shared memory.  This is what sets the occupancy (warps per SM).
     const int FPW = 32 / L;
-    int gl = 0, goff = N / 8, soff = 0;   // workspace starts with the packed level-0 (channel) words
+    // the workspace starts with the packed level-0 (channel) words, [word][frame in warp]: N/8 * FPW words
+    int gl = 0, goff = std::max(1, (N / 8) * FPW / 32), soff = 0;
     P.voff[0] = 0;
     for (int lev = 1; lev <= n - 3; ++lev) {
         int words = (N >> lev) / 8;
