@@ -90,7 +90,8 @@ struct pd_decoder {
     cudaStream_t side[2] = {nullptr, nullptr};
     int force = 0;            // POLAR_B200_FORCE_GENERIC: 1 = CTA-per-frame generic kernel, 2 = path_warp
     const char *kernel_name = "generic";
-    int *d_err = nullptr;
+    int *d_err = nullptr;             // device view of the mapped error flag
+    volatile int *h_err = nullptr;   // host view
     double *dbg_pm = nullptr;
     int32_t *dbg_win = nullptr;
     char *ws_user = nullptr;  // workspace for pd_decode_device (global-memory variant)
@@ -371,6 +372,7 @@ void pd_destroy(pd_decoder *D) {
         cudaFree(sl.d_in); cudaFree(sl.d_out); cudaFree(sl.ws);
     }
     cudaFree(D->ws_user);
+    if (D->h_err) cudaFreeHost((void *)D->h_err);
     for (int i = 0; i < 2; ++i) { if (D->side[i]) { cudaStreamSynchronize(D->side[i]); cudaStreamDestroy(D->side[i]); } if (D->join_ev[i]) cudaEventDestroy(D->join_ev[i]); }
     if (D->fork_ev) cudaEventDestroy(D->fork_ev);
     for (void *p : D->allocs) cudaFree(p);
@@ -469,12 +471,14 @@ int pd_create(const pd_config *c, pd_decoder **out) {
         if ((rc = upload(D, bf, &d.bnd_f)) || (rc = upload(D, bg, &d.bnd_g)) || (rc = upload(D, rf, &d.rec_f)) || (rc = upload(D, rg, &d.rec_g))) return bail(rc);
         d.nb = c->n_boundaries; d.nr = c->n_reconstruction;
     }
-    {
-        void *p = nullptr;
-        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return bail(fail(PD_ECUDA, "cudaMalloc failed"));
-        D->allocs.push_back(p);
-        D->d_err = (int *)p;
-        cudaMemset(p, 0, sizeof(int));
+    {   // error flag in mapped pinned host memory: the kernels write it (over PCIe) only when a symbol is out of range,
+        // the host reads it without a device->host copy
+        void *hp = nullptr, *dp = nullptr;
+        if (cudaHostAlloc(&hp, sizeof(int), cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess)
+            return bail(fail(PD_ECUDA, "cudaHostAlloc (mapped) failed"));
+        D->h_err = (volatile int *)hp;
+        *D->h_err = 0;
+        D->d_err = (int *)dp;
     }
     if ((rc = plan_generic(D))) return bail(rc);
     plan_path_warp(D->dev, &D->path);
@@ -560,10 +564,8 @@ int pd_check(pd_decoder *D, void *cuda_stream) {
     if (!D) return fail(PD_EINVAL, "null decoder");
     CUDA_TRY(cudaSetDevice(D->device));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
-    int h = 0;
-    CUDA_TRY(cudaMemcpy(&h, D->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (h) {
-        cudaMemset(D->d_err, 0, sizeof(int));
+    if (*D->h_err) {
+        *D->h_err = 0;
         return fail(PD_ERANGE, "an input symbol is outside the root lookup table (valid: [0,%d) for the first half, [0,%d) for the second)", D->dev.root_qa, D->dev.root_qb);
     }
     return PD_OK;
