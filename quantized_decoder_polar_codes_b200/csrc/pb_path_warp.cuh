@@ -15,9 +15,10 @@
 // which physical slot holds level d of this logical path.
 //
 // 2L > 16 keys: libstdc++'s std::sort is an introsort whose order of EQUAL keys is algorithm defined (SURVEY
-// App. B1).  A parallel stable rank is used when no two live (< 1e300) keys are equal -- any correct sort then
-// gives the same permutation of the live paths, and the order of dead (1e300 / inf) paths is unobservable --
-// otherwise one lane per frame runs the exact emulation (pb::std_sort_idx).
+// App. B1).  For the plain SCL kinds a parallel stable rank is used when no two live (< 1e300) keys are equal --
+// any correct sort then gives the same permutation of the live paths, and the order of dead (1e300 / inf) paths is
+// unobservable.  Otherwise, and always for the Fast list kinds (their R1 rule reads the ordering held by the
+// destination slot, dead or not), one lane per frame runs the exact emulation (pb::std_sort_idx).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -147,9 +148,11 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
                 }
             }
             if (2 * L > 16) {
-                // exact libstdc++ order needed only if two live keys are equal; decided for the whole warp so that the
-                // frames sharing it stay convergent (the emulation is exact for tie-free frames too)
-                const bool need = __any_sync(kAll, tie);
+                // exact libstdc++ order is needed when two live keys are equal, and always for the Fast list kinds: their
+                // R1 rule flips the bit named by the ordering the DESTINATION slot held before the permutation
+                // (FastSCLDecoder.cpp:197-233), so which dead (PM = inf) path sits in which slot is observable there.
+                // Decided for the whole warp so that the frames sharing it stay convergent.
+                const bool need = d.r1_tmax > 0 || __any_sync(kAll, tie);
                 if (need) {
                     if (me == 0) {
                         int *ord = ORD + gbase * 2;
@@ -510,6 +513,7 @@ inline void plan_path_warp(const Dev &d, PathPlan *pl) {
     int logL = 0;
     while ((1 << logL) < L) logL++;
     if ((1 << logL) != L || L > 32) return;
+    if (d.list && L == 1) return;   // a list decoder with L=1 keeps the list rules (bit = llr<0, REP tie -> all-zero): CTA kernel
     if (N < 32) return;      // sub-word codes stay on the CTA kernel
     PathParams &P = pl->p;
     P = PathParams{};
@@ -525,7 +529,7 @@ inline void plan_path_warp(const Dev &d, PathPlan *pl) {
     P.velems = std::max(soff, 1);
     P.xwords = std::max(N / 32, 1);
     const int FPW = 32 / L;
-    P.scrwords = (L == 1) ? 0 : P.xwords * FPW;
+    P.scrwords = (L == 1) ? 0 : ((P.xwords * FPW + 3) & ~3);   // keeps the fp64 key pairs behind it 16-byte aligned
     P.r1_tmax = d.list ? d.r1_tmax : 0;
     P.r1_off = (((size_t)P.gelems * 32 * sz) + 255) & ~(size_t)255;
     size_t vbytes = (((size_t)P.velems * 32 * sz) + 15) & ~(size_t)15;

@@ -808,6 +808,7 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     int logL = 0;
     while ((1 << logL) < L) logL++;
     if ((1 << logL) != L || L > 8) return;
+    if (d.list && L == 1) return;   // list rules with a single path (bit = llr<0, ...) differ from SC's: generic kernel
     for (int p = 0; p < N - 1; ++p) {
         const NodeTab &t = tabs[p];
         if (t.f_pstride || t.g_pstride) return;
@@ -994,7 +995,7 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     P.gwords = std::max(goff, 1);
     P.vwords = std::max(soff, 1);
     P.xwords = N / 32;
-    P.scrwords = (L == 1) ? 0 : (N / 32) * FPW;
+    P.scrwords = (L == 1) ? 0 : (((N / 32) * FPW + 3) & ~3);
     P.n_ops = (int)ops.size();
     if (getenv("POLAR_B200_DEBUG")) {
         int hist[16] = {0};

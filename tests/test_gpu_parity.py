@@ -125,6 +125,24 @@ def test_both_schedule_interpreters(q, kind, ckw, force, kernel, monkeypatch):
     assert bad == 0, f"{bad}/{x.shape[0]} frames differ ({dec.kernel})"
 
 
+@pytest.mark.parametrize("L", [16, 32])
+@pytest.mark.parametrize("kind", ["FastSCLDecoder", "FastSCLLUTDecoder", "CAFastSCLLUTDecoder"])
+def test_fast_list_r1_exposes_dead_path_order(q, kind, L, monkeypatch):
+    """Regression (found by tools/fuzz_parity.py): in the Fast list kinds the R1 rule flips the bit named by the
+    ordering the DESTINATION slot held before the permutation (FastSCLDecoder.cpp:197-233), so the position of dead
+    (PM = inf) paths after a fork is observable; for 2L > 16 the warp kernel must use the exact std::sort order
+    even when no live keys tie.  Short, low-rate code so that the list fills late and dead paths meet R1 nodes."""
+    monkeypatch.setenv("POLAR_B200_FORCE_GENERIC", "2")
+    ckw = dict(N=64, K=54 if kind.startswith("CA") else 30, L=L, B=200, seed=671108, share=False, per_position=True)
+    if kind.startswith("CA"):
+        ckw["A"] = 30
+    kw, x, _ = common.make_case(kind, **ckw)
+    dec = _build(q, kind, kw)
+    assert dec.kernel == "path_warp"
+    want = po.OracleDecoder(kind, **kw).decode(x)
+    assert (dec.decode(x) == want).all()
+
+
 import real_lut
 
 
