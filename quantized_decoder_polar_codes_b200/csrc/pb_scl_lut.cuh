@@ -58,6 +58,7 @@ struct FastParams {
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
     int vwords, xwords, scrwords;  // shared-memory words per lane: value levels gl+1..top, X; scratch words per warp
+    int scr_off;                   // word offset of the epilogue scratch: its own region, or 0 = on top of the (then dead) value levels
     int gl;                        // value levels 1..gl live in the global (L2-resident) workspace, the rest in shared memory
     int gwords;                    // workspace words per lane
     int voff[kMaxLog + 2];         // word offset of level d inside its home (workspace for d<=gl, shared memory above)
@@ -143,8 +144,8 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
 
     uint32_t *V = sm;                                  // value levels gl+1..top, [word][lane]
     uint32_t *X = V + fp.vwords * 32;                  // partial sums, in place, [word][lane]
-    uint32_t *SCR = X + fp.xwords * 32;                // epilogue scratch [word][frame in warp] (L > 1)
-    uint32_t *RING = SCR + fp.scrwords;                // [kRingChunks][lane][4]
+    uint32_t *SCR = sm + fp.scr_off;                   // epilogue scratch [word][frame in warp] (L > 1)
+    uint32_t *RING = X + fp.xwords * 32 + fp.scrwords; // [kRingChunks][lane][4]
     uint32_t *G = ws + (size_t)blockIdx.x * fp.gwords * 32;   // value levels 1..gl, [word][lane], L2-resident
     double *KS = reinterpret_cast<double *>(RING + kRingChunks * 128);   // [32][2]
     uint32_t *SEL = reinterpret_cast<uint32_t *>(KS + 64);               // [32]
@@ -985,10 +986,13 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     const int FPW = 32 / L;
     // the workspace starts with the packed level-0 (channel) words, [word][frame in warp]: N/8 * FPW words
     int gl = 0, goff = std::max(1, (N / 8) * FPW / 32), soff = 0;
+    // (the Fast-SSC walk is latency bound and gains 7 % from the extra resident warps of a 4-word cut; the plain walk is
+    //  issue bound and indifferent: measured on N=1024, L=8)
+    const int smem_level_words = getenv("POLAR_B200_SMEM_LEVEL_WORDS") ? atoi(getenv("POLAR_B200_SMEM_LEVEL_WORDS")) : (max_special >= 0 ? 4 : 8);
     P.voff[0] = 0;
     for (int lev = 1; lev <= n - 3; ++lev) {
         int words = (N >> lev) / 8;
-        if (words > 8) { P.voff[lev] = goff; goff += words; gl = lev; }
+        if (words > smem_level_words) { P.voff[lev] = goff; goff += words; gl = lev; }
         else { P.voff[lev] = soff; soff += words; }
     }
     P.gl = gl;
@@ -996,6 +1000,9 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     P.vwords = std::max(soff, 1);
     P.xwords = N / 32;
     P.scrwords = (L == 1) ? 0 : (((N / 32) * FPW + 3) & ~3);
+    // the value levels are dead once the last leaf is decided: the epilogue scratch goes on top of them when it fits
+    if (P.scrwords <= P.vwords * 32 && !getenv("POLAR_B200_NO_SCR_ALIAS")) { P.scr_off = 0; P.scrwords = 0; }
+    else P.scr_off = (P.vwords + P.xwords) * 32;
     P.n_ops = (int)ops.size();
     if (getenv("POLAR_B200_DEBUG")) {
         int hist[16] = {0};

@@ -1,3 +1,6 @@
+"""Open-ended random-configuration parity run (needs a GPU): python tests/fuzz_parity.py [seed]
+400 random decoders per seed -- class, N, K, L (also non powers of two), alphabets, table sharing -- CUDA vs the oracle;
+stops at the first mismatch and prints the configuration.  (The bounded version is tests/test_random_configs.py.)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

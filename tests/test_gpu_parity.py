@@ -128,7 +128,7 @@ def test_both_schedule_interpreters(q, kind, ckw, force, kernel, monkeypatch):
 @pytest.mark.parametrize("L", [16, 32])
 @pytest.mark.parametrize("kind", ["FastSCLDecoder", "FastSCLLUTDecoder", "CAFastSCLLUTDecoder"])
 def test_fast_list_r1_exposes_dead_path_order(q, kind, L, monkeypatch):
-    """Regression (found by tools/fuzz_parity.py): in the Fast list kinds the R1 rule flips the bit named by the
+    """Regression (found by tests/fuzz_parity.py): in the Fast list kinds the R1 rule flips the bit named by the
     ordering the DESTINATION slot held before the permutation (FastSCLDecoder.cpp:197-233), so the position of dead
     (PM = inf) paths after a fork is observable; for 2L > 16 the warp kernel must use the exact std::sort order
     even when no live keys tie.  Short, low-rate code so that the list fills late and dead paths meet R1 nodes."""
