@@ -26,108 +26,118 @@ namespace pb {
 // reproduced so that the order of equal keys matches the reference build bit for bit.
 // Sub-ranges produced by the partition step are disjoint, so processing them from an explicit stack in a
 // different order than the recursion does not change the result.
-template <typename IdxT>
-__device__ inline void ss_unguarded_linear_insert(IdxT *a, int last, const double *key) {
-    IdxT val = a[last];
+// The algorithm is written once over an accessor (get/set of element i) and a strict-weak `less` on element VALUES,
+// so that the same code sorts an index array through a key table (PtrAcc/KeyLess, below) and the packed, lane-strided
+// shared-memory arrays of the warp kernels.
+template <class A, class Less>
+__device__ inline void ss_unguarded_linear_insert(A a, int last, Less less) {
+    const typename A::V val = a.get(last);
     int next = last - 1;
-    while (key[val] < key[a[next]]) { a[last] = a[next]; last = next; --next; }
-    a[last] = val;
+    for (;;) {
+        const typename A::V nv = a.get(next);
+        if (!less(val, nv)) break;
+        a.set(last, nv);
+        last = next;
+        --next;
+    }
+    a.set(last, val);
 }
-template <typename IdxT>
-__device__ inline void ss_insertion_sort(IdxT *a, int first, int last, const double *key) {
+template <class A, class Less>
+__device__ inline void ss_insertion_sort(A a, int first, int last, Less less) {
     if (first == last) return;
     for (int i = first + 1; i != last; ++i) {
-        if (key[a[i]] < key[a[first]]) {
-            IdxT val = a[i];
-            for (int k = i; k > first; --k) a[k] = a[k - 1];
-            a[first] = val;
+        const typename A::V val = a.get(i);
+        if (less(val, a.get(first))) {
+            for (int k = i; k > first; --k) a.set(k, a.get(k - 1));
+            a.set(first, val);
         } else {
-            ss_unguarded_linear_insert(a, i, key);
+            ss_unguarded_linear_insert(a, i, less);
         }
     }
 }
-template <typename IdxT>
-__device__ inline void ss_push_heap(IdxT *a, int first, int hole, int top, IdxT value, const double *key) {
+template <class A, class Less>
+__device__ inline void ss_push_heap(A a, int first, int hole, int top, typename A::V value, Less less) {
     int parent = (hole - 1) / 2;
-    while (hole > top && key[a[first + parent]] < key[value]) {
-        a[first + hole] = a[first + parent];
+    while (hole > top && less(a.get(first + parent), value)) {
+        a.set(first + hole, a.get(first + parent));
         hole = parent;
         parent = (hole - 1) / 2;
     }
-    a[first + hole] = value;
+    a.set(first + hole, value);
 }
-template <typename IdxT>
-__device__ inline void ss_adjust_heap(IdxT *a, int first, int hole, int len, IdxT value, const double *key) {
+template <class A, class Less>
+__device__ inline void ss_adjust_heap(A a, int first, int hole, int len, typename A::V value, Less less) {
     const int top = hole;
     int child = hole;
     while (child < (len - 1) / 2) {
         child = 2 * (child + 1);
-        if (key[a[first + child]] < key[a[first + child - 1]]) child--;
-        a[first + hole] = a[first + child];
+        if (less(a.get(first + child), a.get(first + child - 1))) child--;
+        a.set(first + hole, a.get(first + child));
         hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2) {
         child = 2 * (child + 1);
-        a[first + hole] = a[first + child - 1];
+        a.set(first + hole, a.get(first + child - 1));
         hole = child - 1;
     }
-    ss_push_heap(a, first, hole, top, value, key);
+    ss_push_heap(a, first, hole, top, value, less);
 }
-template <typename IdxT>
-__device__ inline void ss_heapsort(IdxT *a, int first, int last, const double *key) {
+template <class A, class Less>
+__device__ inline void ss_heapsort(A a, int first, int last, Less less) {
     int len = last - first;
     if (len >= 2) {
         int parent = (len - 2) / 2;
         for (;;) {
-            IdxT value = a[first + parent];
-            ss_adjust_heap(a, first, parent, len, value, key);
+            const typename A::V value = a.get(first + parent);
+            ss_adjust_heap(a, first, parent, len, value, less);
             if (parent == 0) break;
             parent--;
         }
     }
     while (last - first > 1) {
         --last;
-        IdxT value = a[last];
-        a[last] = a[first];
-        ss_adjust_heap(a, first, 0, last - first, value, key);
+        const typename A::V value = a.get(last);
+        a.set(last, a.get(first));
+        ss_adjust_heap(a, first, 0, last - first, value, less);
     }
 }
-template <typename IdxT>
-__device__ inline void ss_swap(IdxT *a, int i, int j) { IdxT t = a[i]; a[i] = a[j]; a[j] = t; }
+template <class A>
+__device__ inline void ss_swap(A a, int i, int j) { const typename A::V t = a.get(i); a.set(i, a.get(j)); a.set(j, t); }
 
-template <typename IdxT>
-__device__ void std_sort_idx(IdxT *a, int n, const double *key) {
+// STK: capacity of the explicit range stack (one entry per pending right-hand partition: <= 2*log2(n) + 1)
+template <int STK, class A, class Less>
+__device__ inline void std_sort_acc(A a, int n, Less less) {
     if (n <= 1) return;
     if (n > 16) {
         int lg = 0;
         for (int t = n; t > 1; t >>= 1) lg++;
-        int stk_f[40], stk_l[40], stk_d[40];
+        int stk_f[STK], stk_l[STK], stk_d[STK];
         int sp = 0;
         stk_f[0] = 0; stk_l[0] = n; stk_d[0] = 2 * lg; sp = 1;
         while (sp > 0) {
             --sp;
             int first = stk_f[sp], last = stk_l[sp], depth = stk_d[sp];
             while (last - first > 16) {
-                if (depth == 0) { ss_heapsort(a, first, last, key); break; }
+                if (depth == 0) { ss_heapsort(a, first, last, less); break; }
                 --depth;
                 int mid = first + (last - first) / 2;
                 // __move_median_to_first(first, first+1, mid, last-1)
                 int ia = first + 1, ib = mid, ic = last - 1;
-                double ka = key[a[ia]], kb = key[a[ib]], kc = key[a[ic]];
-                if (ka < kb) {
-                    if (kb < kc) ss_swap(a, first, ib);
-                    else if (ka < kc) ss_swap(a, first, ic);
+                const typename A::V ka = a.get(ia), kb = a.get(ib), kc = a.get(ic);
+                if (less(ka, kb)) {
+                    if (less(kb, kc)) ss_swap(a, first, ib);
+                    else if (less(ka, kc)) ss_swap(a, first, ic);
                     else ss_swap(a, first, ia);
-                } else if (ka < kc) ss_swap(a, first, ia);
-                else if (kb < kc) ss_swap(a, first, ic);
+                } else if (less(ka, kc)) ss_swap(a, first, ia);
+                else if (less(kb, kc)) ss_swap(a, first, ic);
                 else ss_swap(a, first, ib);
                 // __unguarded_partition(first+1, last, pivot = first)
                 int lo = first + 1, hi = last;
-                double kp = key[a[first]];
+                const typename A::V kp = a.get(first);
                 for (;;) {
-                    while (key[a[lo]] < kp) ++lo;
+                    while (less(a.get(lo), kp)) ++lo;
                     --hi;
-                    while (kp < key[a[hi]]) --hi;
+                    while (less(kp, a.get(hi))) --hi;
                     if (!(lo < hi)) break;
                     ss_swap(a, lo, hi);
                     ++lo;
@@ -137,11 +147,29 @@ __device__ void std_sort_idx(IdxT *a, int n, const double *key) {
                 last = lo;
             }
         }
-        ss_insertion_sort(a, 0, 16, key);
-        for (int i = 16; i < n; ++i) ss_unguarded_linear_insert(a, i, key);
+        ss_insertion_sort(a, 0, 16, less);
+        for (int i = 16; i < n; ++i) ss_unguarded_linear_insert(a, i, less);
     } else {
-        ss_insertion_sort(a, 0, n, key);
+        ss_insertion_sort(a, 0, n, less);
     }
+}
+
+template <typename IdxT>
+struct PtrAcc {
+    using V = IdxT;
+    IdxT *p;
+    __device__ __forceinline__ V get(int i) const { return p[i]; }
+    __device__ __forceinline__ void set(int i, V v) const { p[i] = v; }
+};
+template <typename IdxT>
+struct KeyLess {
+    const double *key;
+    __device__ __forceinline__ bool operator()(IdxT x, IdxT y) const { return key[x] < key[y]; }
+};
+// index array `a` sorted by key[a[i]]
+template <typename IdxT>
+__device__ void std_sort_idx(IdxT *a, int n, const double *key) {
+    std_sort_acc<40>(PtrAcc<IdxT>{a}, n, KeyLess<IdxT>{key});
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -87,7 +88,18 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory");
 }
 
-__device__ __noinline__ void sort_idx_noinline(int *idx, int n, const double *key) { std_sort_idx(idx, n, key); }
+// R1 nodes of the list Fast decoders: elements packed as rank<<5 | index, one column of a [element][32 lanes] array of
+// 16-bit words; std::sort order under "rank < rank" (equal ranks = equal |llr|: libstdc++'s introsort order)
+struct R1Acc {
+    using V = unsigned short;
+    unsigned short *p;   // element i at p[i * 32]
+    __device__ __forceinline__ V get(int i) const { return p[i * 32]; }
+    __device__ __forceinline__ void set(int i, V v) const { p[i * 32] = v; }
+};
+struct R1Less {
+    __device__ __forceinline__ bool operator()(unsigned short x, unsigned short y) const { return (x >> 5) < (y >> 5); }
+};
+__device__ __noinline__ void sort_r1_packed(unsigned short *col, int n) { std_sort_acc<16>(R1Acc{col}, n, R1Less{}); }
 
 struct RingState {
     unsigned fetch_off;   // byte offset (within the stream) of the next chunk to prefetch
@@ -107,8 +119,15 @@ __device__ __forceinline__ uint4 ring_next_chunk(RingState &rs, unsigned ring_la
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_lane + slot * 512u));
     return v;
 }
-__device__ __noinline__ uint4 ring_next_chunk_outlined(RingState *rs, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
-    return ring_next_chunk(*rs, ring_lane, stream_lane, stream_bytes);
+// out-of-line refill for the Fast-SSC variant (~40 consumption sites): everything travels in registers, the caller
+// advances the ring state itself
+__device__ __noinline__ uint4 ring_fetch_outlined(unsigned fetch_off, unsigned chunk_no, unsigned ring_lane, const char *stream_lane) {
+    const unsigned slot = chunk_no & (kRingChunks - 1);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(ring_lane + ((slot + kRingChunks - 1) & (kRingChunks - 1)) * 512u), "l"(stream_lane + fetch_off));
+    cp_async_wait<kRingChunks - 1>();
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_lane + slot * 512u));
+    return v;
 }
 struct LineState {
     RingState rs;
@@ -120,9 +139,6 @@ __device__ __forceinline__ uint32_t next_line_inl(LineState &ls, unsigned ring_l
     const uint32_t v = ls.q == 0 ? ls.cur.x : ls.q == 1 ? ls.cur.y : ls.q == 2 ? ls.cur.z : ls.cur.w;
     ++ls.q;
     return v;
-}
-__device__ __noinline__ uint32_t next_line_outlined(LineState *ls, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
-    return next_line_inl(*ls, ring_lane, stream_lane, stream_bytes);
 }
 
 // 4 symbol bytes -> 4 nibbles (16 bits)
@@ -151,6 +167,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     uint32_t *SEL = reinterpret_cast<uint32_t *>(KS + 64);               // [32]
     double *R1S = reinterpret_cast<double *>(SEL + 32);                  // [7][32] smallest |llr| of an R1 node (Fast kinds)
     uint32_t *R1Q = reinterpret_cast<uint32_t *>(R1S + 7 * 32);          // [7][32] their positions
+    unsigned short *R1P = reinterpret_cast<unsigned short *>(R1S);       // [32][32] packed sort keys of an R1 node (dead before R1S/R1Q are written)
 
     // ---- table stream.  Every f/g table (one 128-byte line = 16x16 nibbles) and every leaf LLR row (16 doubles)
     //      is consumed exactly once per pass, in a fixed order, and lane l only ever needs word l of a line.  The
@@ -165,12 +182,25 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     // the Fast-SSC variant has ~40 consumption sites: there the stream accessors are real (out-of-line) functions so
     // that the hot code stays inside the instruction cache; the plain variant inlines them
     auto next_chunk = [&]() -> uint4 {
-        if (FAST && L > 1) return ring_next_chunk_outlined(&ls.rs, ring_lane, stream_lane, stream_bytes);
+        if (FAST && L > 1) {
+            const uint4 v = ring_fetch_outlined(ls.rs.fetch_off, ls.rs.chunk_no, ring_lane, stream_lane);
+            ls.rs.fetch_off += 512u;
+            if (ls.rs.fetch_off == stream_bytes) ls.rs.fetch_off = 0;
+            ++ls.rs.chunk_no;
+            return v;
+        }
         return ring_next_chunk(ls.rs, ring_lane, stream_lane, stream_bytes);
     };
-    // upper-level steps and special nodes take their lines one at a time out of the current chunk
+    // upper-level steps and special nodes take their lines one at a time out of the current chunk.  In the Fast-SSC
+    // variant `cur` is a queue with the next line in .x (no selects at the many call sites)
     auto next_line = [&]() -> uint32_t {
-        if (FAST && L > 1) return next_line_outlined(&ls, ring_lane, stream_lane, stream_bytes);
+        if (FAST && L > 1) {
+            if (ls.q == 4) { ls.cur = next_chunk(); ls.q = 0; }
+            const uint32_t v = ls.cur.x;
+            ls.cur.x = ls.cur.y; ls.cur.y = ls.cur.z; ls.cur.z = ls.cur.w;
+            ++ls.q;
+            return v;
+        }
         return next_line_inl(ls, ring_lane, stream_lane, stream_bytes);
     };
     // eight f (or g) lookups for one word of symbols: out nibble k = T[u_k][a_k][b_k] with a_k / b_k nibble k of A / Bv.
@@ -403,7 +433,8 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         auto special = [&](int spt, int dd, uint32_t node) {
             const int temp = N >> dd;
             // the node's LLR lines start on a chunk boundary: four elements per chunk, no per-line bookkeeping
-            if (!(L == 1 && spt == 0)) ls.q = 4;   // (the non-list R0 reads no LLRs and has no lines)
+            // (the non-list R0 has no lines; the list R1 takes its rank lines one by one like the upper-level steps)
+            if (!(L == 1 && spt == 0) && !(L > 1 && spt == 1)) ls.q = 4;
             uint4 ech = make_uint4(0, 0, 0, 0);
             auto elem_line = [&](int j) -> uint32_t {
                 if (PB_EXP_LINE) return next_line();
@@ -411,7 +442,12 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 return (j & 3) == 0 ? ech.x : (j & 3) == 1 ? ech.y : (j & 3) == 2 ? ech.z : ech.w;
             };
             // a node of 2 elements leaves half a chunk: the following ops' lines continue there
-            auto elem_done = [&]() { if (!PB_EXP_LINE && (temp & 3)) { ls.cur = ech; ls.q = temp & 3; } };
+            auto elem_done = [&]() {
+                if (PB_EXP_LINE || (temp & 3) == 0) return;
+                ls.q = 2;                                                  // temp == 2
+                if (FAST && L > 1) { ls.cur.x = ech.z; ls.cur.y = ech.w; }  // queue form: next line in .x
+                else ls.cur = ech;
+            };
             const uint32_t full = temp >= 32 ? 0xffffffffu : ((1u << temp) - 1u);
             if (L == 1) {
                 // PD/src/FastSCLUT.cpp:43-106
@@ -448,16 +484,13 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 }
                 return;
             }
-            // one pass over the node's elements, in position order (the fp64 sums are serial in the reference):
-            //   R0  (PD/src/FastSCLLUTDecoder.cpp:83-93)   PM += (l<0)|l|
-            //   REP (:169-184)                             candidates all-0 / all-1: a0 += (l<0)|l|, a1 += (l>=0)|l|
-            //   R1  (:98-121, temp <= 32)                  hard decisions + |l| for the argsort
             int rounds = 1;
             uint32_t dec = 0, rowp = (uint32_t)me;
             double a0 = PM, a1 = PM;
-            double key[32];
-            int idx[32];
-            {
+            if (spt != 1) {
+                // one pass over the node's elements, in position order (the fp64 sums are serial in the reference):
+                //   R0  (PD/src/FastSCLLUTDecoder.cpp:83-93)   PM += (l<0)|l|
+                //   REP (:169-184)                             candidates all-0 / all-1: a0 += (l<0)|l|, a1 += (l>=0)|l|
                 uint32_t sw = 0;
                 for (int j = 0; j < temp; ++j) {
                     if ((j & 7) == 0) sw = node_word(dd, j >> 3);
@@ -465,40 +498,56 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                     const double al = fabs(l);
                     if (spt == 0) {
                         PM += (double)(float)(l < 0) * al;
-                    } else if (spt == 2) {
+                    } else {
                         a0 += (double)(l < 0) * al;
                         a1 += (double)(l >= 0) * al;
-                    } else {
-                        key[j & 31] = al;
-                        idx[j & 31] = j;
-                        dec |= (l < 0 ? 1u : 0u) << (j & 31);
                     }
                 }
-            }
-            elem_done();
-            if (spt == 0) rounds = 0;
-            if (spt == 1) {
-                // argsort(abs_llr) in libstdc++'s order; only its first min(L-1,temp) entries are ever used
+                elem_done();
+                if (spt == 0) rounds = 0;
+            } else {
+                // R1 (:98-121, temp <= 32): hard decisions and argsort(|l|), of which only the first min(L-1,temp)
+                // entries are used.  The order of the |l| of a node depends only on how the <= 32*16 table values
+                // compare, so the host ships their dense ranks (equal values share a rank) and the sign bits, 16 bits
+                // per (element, symbol), four elements per line: the sort runs on small integers in shared memory,
+                // [element][lane] (conflict free), packed as rank<<5 | element.
                 rounds = (L - 1 < temp) ? L - 1 : temp;
                 __syncwarp();
+                uint32_t sw = 0, line = 0;
+                for (int j = 0; j < temp; ++j) {
+                    if ((j & 3) == 0) line = next_line();
+                    if ((j & 7) == 0) sw = node_word(dd, j >> 3);
+                    const uint32_t sym = nib(sw, j & 7);
+                    const uint32_t w = __shfl_sync(kFull, line, (j & 3) * 8 + (int)(sym >> 1));
+                    const uint32_t e = (sym & 1u) ? (w >> 16) : (w & 0xffffu);
+                    dec |= (e & 1u) << j;
+                    R1P[j * 32 + lane] = (unsigned short)(((e >> 1) << 5) | (uint32_t)j);
+                }
+                unsigned long long qs = 0;   // the `rounds` least reliable positions, 5 bits each
                 if (temp <= 16) {
-                    // <= 16 elements: std::sort is an insertion sort = stable, so entry k is the k-th smallest by
-                    // (value, index): repeated min extraction with independent loads instead of a dependent sort chain
-                    uint32_t taken = 0;
+                    // <= 16 elements: std::sort is an insertion sort = stable, i.e. ascending (rank, element) = ascending
+                    // packed value: repeated extraction of the next larger one
+                    int prev = -1;
                     for (int k = 0; k < rounds; ++k) {
-                        double best = 0;
-                        int bj = -1;
+                        int best = 0x7fffffff;
                         for (int j = 0; j < temp; ++j) {
-                            const double kj = key[j];
-                            if (!((taken >> j) & 1u) && (bj < 0 || kj < best)) { best = kj; bj = j; }
+                            const int v = (int)R1P[j * 32 + lane];
+                            if (v > prev && v < best) best = v;
                         }
-                        taken |= 1u << bj;
-                        R1S[k * 32 + lane] = best;
-                        R1Q[k * 32 + lane] = (uint32_t)bj;
+                        prev = best;
+                        qs |= (unsigned long long)(best & 31) << (5 * k);
                     }
                 } else {
-                    sort_idx_noinline(idx, temp, key);
-                    for (int k = 0; k < rounds; ++k) { R1S[k * 32 + lane] = key[idx[k]]; R1Q[k * 32 + lane] = (uint32_t)idx[k]; }
+                    sort_r1_packed(R1P + lane, temp);     // libstdc++'s introsort order of equal ranks
+                    for (int k = 0; k < rounds; ++k) qs |= (unsigned long long)(R1P[k * 32 + lane] & 31u) << (5 * k);
+                }
+                __syncwarp();                             // R1P shares its storage with R1S / R1Q
+                for (int k = 0; k < rounds; ++k) {
+                    const int qk = (int)((qs >> (5 * k)) & 31ull);
+                    const uint32_t sym = nib(node_word(dd, qk >> 3), qk & 7);
+                    const uint32_t row = __ldg(d.llr_off + (size_t)(dd - 1) * N + node * (uint32_t)temp + qk);
+                    R1S[k * 32 + lane] = fabs(__ldg(d.llr + row + sym));
+                    R1Q[k * 32 + lane] = (uint32_t)qk;
                 }
                 __syncwarp();
             }
@@ -864,6 +913,39 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         memcpy(line, &llr[llr_off[r]], (size_t)len * sizeof(double));
         stream.insert(stream.end(), line, line + 32);
     };
+    // list R1 node: dense ranks of |llr| over all (element, symbol) of the node + the sign bits, 16 bits per entry
+    // ((rank << 1) | (llr < 0)), entry (j, s) in half (s & 1) of word (j & 3) * 8 + (s >> 1) of line j >> 2
+    auto push_r1_ranks = [&](int depth, int node) {
+        const int temp = N >> depth;
+        std::vector<double> vals;
+        for (int j = 0; j < temp; ++j) {
+            const int64_t r = (int64_t)(depth - 1) * N + node * temp + j;
+            const int len = (int)(llr_off64[r + 1] - llr_off64[r]);
+            if (len > 16) { ok = false; return; }
+            for (int sidx = 0; sidx < len; ++sidx) {
+                const double v = llr[llr_off[r] + sidx];
+                if (v != v) { ok = false; return; }   // NaN has no rank: generic kernel
+                vals.push_back(std::fabs(v));
+            }
+        }
+        std::sort(vals.begin(), vals.end());
+        vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+        for (int j0 = 0; j0 < temp; j0 += 4) {
+            uint32_t line[32];
+            memset(line, 0, sizeof line);
+            for (int j = j0; j < std::min(temp, j0 + 4); ++j) {
+                const int64_t r = (int64_t)(depth - 1) * N + node * temp + j;
+                const int len = (int)(llr_off64[r + 1] - llr_off64[r]);
+                for (int sidx = 0; sidx < len; ++sidx) {
+                    const double v = llr[llr_off[r] + sidx];
+                    const uint32_t rank = (uint32_t)(std::lower_bound(vals.begin(), vals.end(), std::fabs(v)) - vals.begin());
+                    const uint32_t e = (rank << 1) | (v < 0 ? 1u : 0u);
+                    line[(j & 3) * 8 + (sidx >> 1)] |= e << (16 * (sidx & 1));
+                }
+            }
+            stream.insert(stream.end(), line, line + 32);
+        }
+    };
     std::function<bool(int, int)> plain = [&](int depth, int node) -> bool {   // no special node in this subtree
         if (depth >= n) return true;
         if (is_special(depth, node) >= 0) return false;
@@ -875,7 +957,8 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         if (st >= 0) {
             if (L > 1 && st == 1) { has_r1 = true; if (temp > 32) ok = false; }
             emit(FOP_SP, depth, st, (uint32_t)node);
-            if (!(L == 1 && st == 0))
+            if (L > 1 && st == 1) push_r1_ranks(depth, node);
+            else if (!(L == 1 && st == 0))
                 for (int j = 0; j < temp; ++j) push_llr_row(depth - 1, node * temp + j);
             return;
         }
@@ -940,7 +1023,8 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
             stream.insert(stream.end(), line, line + 32);
         }
         const uint32_t oty = ops[i].x & 0xffu;
-        if (oty == FOP_SUB8 || (oty == FOP_SP && !op_lines[i].empty()))
+        const bool list_r1 = oty == FOP_SP && L > 1 && ((ops[i].x >> 16) & 0xffu) == 1u;
+        if (oty == FOP_SUB8 || (oty == FOP_SP && !op_lines[i].empty() && !list_r1))
             while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
         stream.insert(stream.end(), op_lines[i].begin(), op_lines[i].end());
     }
