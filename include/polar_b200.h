@@ -157,6 +157,20 @@ void pd_sim_destroy(pd_sim *sim);
 int pd_sim_generate(pd_sim *sim, double sigma, int64_t B, uint64_t seed, uint64_t first_frame,
                     uint8_t *dev_msg, void *dev_out, void *cuda_stream);
 
+/* Batched encoder side of the same object: what the drivers call on the PolarBDEnc package, which is
+ * imported by all four drivers (mainFPDecoder.py:12-13,56-57,102-105) but absent from the reference tree.  Bits are one
+ * byte each (0/1), as in the drivers' numpy arrays.
+ *   PD_ENC_POLAR      in [B][K] -> out [B][N]   PolarEnc(N,K,frozenbits,msgbits).encode: u[msgbits] = in, x = u F^(x)n
+ *                                               (natural order, the butterfly of PD/src/FastSCDecoder.cpp:153-164)
+ *   PD_ENC_CRC        in [B][A] -> out [B][K]   CRCEnc(crc_n,crc_p).encode: in || CRC::encoding(in) (PD/src/utils.cpp:77-93)
+ *   PD_ENC_CRC_POLAR  in [B][A] -> out [B][N]   both in one pass
+ * pd_sim_encode takes host buffers (copies inside), pd_sim_encode_device device buffers, asynchronous on cuda_stream. */
+#define PD_ENC_POLAR 0
+#define PD_ENC_CRC 1
+#define PD_ENC_CRC_POLAR 2
+int pd_sim_encode(pd_sim *sim, int mode, const uint8_t *in, int64_t B, uint8_t *out);
+int pd_sim_encode_device(pd_sim *sim, int mode, const uint8_t *dev_in, int64_t B, uint8_t *dev_out, void *cuda_stream);
+
 /* Kernels launched by this library on the calling process so far (bench.py reports it as gpu_launches). */
 int64_t pd_launch_count(void);
 /* Name of the kernel variant pd_decode* uses for this decoder ("generic", "scl_lut_warp", ...). */

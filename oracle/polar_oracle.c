@@ -201,6 +201,28 @@ static void p_crc(const uint8_t *info, int len, const int32_t *poly, int crc_n, 
     free(u);
 }
 
+/* Encoder side (the PolarBDEnc package the drivers import is not in the reference tree; its conventions are fixed by
+ * the code that IS there): CRC = msg || CRC::encoding(msg) (utils.cpp:77-93); polar encode = u[msgbits] = word,
+ * x = u F^{(x)n} in natural order with the butterfly of the decoders' own re-encode (FastSCDecoder.cpp:153-164).
+ * in [B][len] bits, out [B][len+crc_n]. */
+void po_crc_attach(const uint8_t *in, int64_t B, int len, const int32_t *poly, int crc_n, uint8_t *out) {
+    for (int64_t f = 0; f < B; ++f) {
+        memcpy(out + f * (len + crc_n), in + f * len, (size_t)len);
+        p_crc(in + f * len, len, poly, crc_n, out + f * (len + crc_n) + len);
+    }
+}
+/* in [B][K] bits placed at info_pos[0..K), out [B][N] */
+void po_polar_encode(const uint8_t *in, int64_t B, int K, const int32_t *info_pos, int N, uint8_t *out) {
+    for (int64_t f = 0; f < B; ++f) {
+        uint8_t *x = out + f * N;
+        memset(x, 0, (size_t)N);
+        for (int k = 0; k < K; ++k) x[info_pos[k]] = in[f * K + k];
+        for (int m = 1; m < N; m *= 2)
+            for (int i = 0; i < N; i += 2 * m)
+                for (int j = 0; j < m; ++j) x[i + j] = x[i + j] ^ x[i + m + j];
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 typedef struct {
     const po_config *c;

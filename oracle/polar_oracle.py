@@ -60,6 +60,10 @@ def lib():
         _lib = C.CDLL(build_port())
         _lib.po_decode.restype = C.c_int
         _lib.po_decode.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.po_crc_attach.restype = None
+        _lib.po_crc_attach.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.po_polar_encode.restype = None
+        _lib.po_polar_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib.po_std_sort_idx.restype = None
         _lib.po_std_sort_idx.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     return _lib
@@ -202,3 +206,22 @@ def load_reference():
         _ref_mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(_ref_mod)
     return _ref_mod
+
+
+def crc_attach(msg, crc_n, crc_p):
+    """msg || CRC::encoding(msg) (PD/src/utils.cpp:77-93); crc_p = generator exponents as the drivers pass them."""
+    m = np.ascontiguousarray(np.atleast_2d(msg), dtype=np.uint8)
+    poly = np.zeros(int(crc_n) + 1, np.int32)
+    poly[np.asarray(crc_p, dtype=np.int64)] = 1
+    out = np.empty((m.shape[0], m.shape[1] + int(crc_n)), np.uint8)
+    lib().po_crc_attach(m.ctypes.data, m.shape[0], m.shape[1], poly.ctypes.data, int(crc_n), out.ctypes.data)
+    return out
+
+
+def polar_encode(word, msg_positions, N):
+    """u[msg_positions] = word, x = u F^{(x)n} (natural order, the decoders' re-encode butterfly, FastSCDecoder.cpp:153-164)."""
+    w = np.ascontiguousarray(np.atleast_2d(word), dtype=np.uint8)
+    pos = np.ascontiguousarray(msg_positions, dtype=np.int32)
+    out = np.empty((w.shape[0], int(N)), np.uint8)
+    lib().po_polar_encode(w.ctypes.data, w.shape[0], w.shape[1], pos.ctypes.data, int(N), out.ctypes.data)
+    return out

@@ -39,6 +39,8 @@ def lib():
         L.pd_sim_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.pd_sim_destroy.argtypes = [C.c_void_p]
         L.pd_sim_generate.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pd_sim_encode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+        L.pd_sim_encode_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

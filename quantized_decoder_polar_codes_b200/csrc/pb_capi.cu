@@ -22,6 +22,7 @@
 #include "pb_scl_lut.cuh"
 #include "pb_path_warp.cuh"
 #include "pb_sim.cuh"
+#include "pb_enc.cuh"
 
 using namespace pb;
 
@@ -640,6 +641,7 @@ int pd_count_errors(const uint8_t *dev_decoded, const uint8_t *dev_truth, int64_
 struct pd_sim {
     SimDev dev{};
     int device = 0;
+    const EncWord *enc_tab = nullptr;   // N <= 1024: per-word deposit description of the register encoder
     std::vector<void *> allocs;
 };
 extern "C" {
@@ -701,6 +703,20 @@ int pd_sim_create(const pd_sim_config *c, pd_sim **out) {
         }
     }
     if ((rc = up(rem.data(), rem.size() * 4, (const void **)&d.crc_rem))) { pd_sim_destroy(S); return rc; }
+    if (N <= 1024) {
+        std::vector<EncWord> tab(32);
+        memset(tab.data(), 0, tab.size() * sizeof(EncWord));
+        uint32_t before = 0;
+        for (int w = 0; w < N / 32; ++w) {
+            uint32_t m = 0;
+            for (int b = 0; b < 32; ++b) if (c->frozen_bits[32 * w + b] == 0) m |= 1u << b;
+            tab[w].mask = m;
+            tab[w].kstart = before;
+            enc_expand_masks(m, tab[w].mv);
+            before += (uint32_t)__builtin_popcount(m);
+        }
+        if ((rc = up(tab.data(), tab.size() * sizeof(EncWord), (const void **)&S->enc_tab))) { pd_sim_destroy(S); return rc; }
+    }
     if (c->edges) {
         if ((rc = up(c->edges, (size_t)c->n_edges * 8, (const void **)&d.edges)) ||
             (rc = up(c->chan_lut, (size_t)(c->n_edges - 1), (const void **)&d.chan_lut))) { pd_sim_destroy(S); return rc; }
@@ -723,6 +739,62 @@ int pd_sim_generate(pd_sim *S, double sigma, int64_t B, uint64_t seed, uint64_t 
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return PD_OK;
+}
+
+static int enc_lengths(const pd_sim *S, int mode, int *in_len, int *out_len) {
+    switch (mode) {
+    case PD_ENC_POLAR: *in_len = S->dev.K; *out_len = S->dev.N; return PD_OK;
+    case PD_ENC_CRC: *in_len = S->dev.A; *out_len = S->dev.K; break;
+    case PD_ENC_CRC_POLAR: *in_len = S->dev.A; *out_len = S->dev.N; break;
+    default: return fail(PD_EINVAL, "unknown encoder mode %d", mode);
+    }
+    if (S->dev.crc_n <= 0) return fail(PD_EINVAL, "this pd_sim was created without a CRC (crc_n = 0)");
+    return PD_OK;
+}
+
+int pd_sim_encode_device(pd_sim *S, int mode, const uint8_t *dev_in, int64_t B, uint8_t *dev_out, void *cuda_stream) {
+    if (!S || (B > 0 && (!dev_in || !dev_out))) return fail(PD_EINVAL, "null argument");
+    int in_len = 0, out_len = 0, rc;
+    if ((rc = enc_lengths(S, mode, &in_len, &out_len))) return rc;
+    if (B <= 0) return PD_OK;
+    CUDA_TRY(cudaSetDevice(S->device));
+    const int threads = 256, wpb = threads / 32;
+    const size_t smem = (size_t)wpb * (S->dev.N / 32) * 4;
+    const int grid = (int)std::min<int64_t>((B + wpb - 1) / wpb, (int64_t)148 * 8);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(dev_in) & 3) == 0 && (reinterpret_cast<uintptr_t>(dev_out) & 15) == 0) ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (mode == PD_ENC_CRC) encode_kernel<ENC_CRC><<<grid, threads, smem, st>>>(S->dev, dev_in, dev_out, B, vec_ok);
+    else if (S->enc_tab && mode == PD_ENC_POLAR) encode_words_kernel<ENC_POLAR><<<grid, threads, 0, st>>>(S->dev, S->enc_tab, dev_in, dev_out, B, vec_ok);
+    else if (S->enc_tab) encode_words_kernel<ENC_CRC_POLAR><<<grid, threads, 0, st>>>(S->dev, S->enc_tab, dev_in, dev_out, B, vec_ok);
+    else if (mode == PD_ENC_POLAR) encode_kernel<ENC_POLAR><<<grid, threads, smem, st>>>(S->dev, dev_in, dev_out, B, vec_ok);
+    else encode_kernel<ENC_CRC_POLAR><<<grid, threads, smem, st>>>(S->dev, dev_in, dev_out, B, vec_ok);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PD_OK;
+}
+
+int pd_sim_encode(pd_sim *S, int mode, const uint8_t *in, int64_t B, uint8_t *out) {
+    if (!S || (B > 0 && (!in || !out))) return fail(PD_EINVAL, "null argument");
+    int in_len = 0, out_len = 0, rc;
+    if ((rc = enc_lengths(S, mode, &in_len, &out_len))) return rc;
+    if (B <= 0) return PD_OK;
+    CUDA_TRY(cudaSetDevice(S->device));
+    // bounded staging: chunks of <= 32 MiB of output
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)32 << 20) / out_len));
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    if (cudaMalloc(&d_in, (size_t)chunk * in_len) != cudaSuccess) return fail(PD_ENOMEM, "cudaMalloc failed");
+    if (cudaMalloc(&d_out, (size_t)chunk * out_len) != cudaSuccess) { cudaFree(d_in); return fail(PD_ENOMEM, "cudaMalloc failed"); }
+    rc = PD_OK;
+    for (int64_t f0 = 0; f0 < B && rc == PD_OK; f0 += chunk) {
+        const int64_t b = std::min(chunk, B - f0);
+        if (cudaMemcpyAsync(d_in, in + (size_t)f0 * in_len, (size_t)b * in_len, cudaMemcpyHostToDevice, 0) != cudaSuccess) { rc = fail(PD_ECUDA, "H2D copy failed"); break; }
+        if ((rc = pd_sim_encode_device(S, mode, d_in, b, d_out, nullptr))) break;
+        if (cudaMemcpyAsync(out + (size_t)f0 * out_len, d_out, (size_t)b * out_len, cudaMemcpyDeviceToHost, 0) != cudaSuccess) { rc = fail(PD_ECUDA, "D2H copy failed"); break; }
+        if (cudaStreamSynchronize(0) != cudaSuccess) { rc = fail(PD_ECUDA, "encode failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
 }
 
 void *pd_host_alloc(size_t bytes) {
