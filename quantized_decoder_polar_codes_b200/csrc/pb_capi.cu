@@ -31,6 +31,19 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 
+// SM count of the current device (grid sizing of the streaming kernels), cached
+int current_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cache[dev].load();
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev].store(v);
+    }
+    return v;
+}
+
 int fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -629,7 +642,7 @@ int pd_count_errors(const uint8_t *dev_decoded, const uint8_t *dev_truth, int64_
     if (B <= 0) return PD_OK;
     if (!dev_decoded || !dev_truth || !dev_counters || len < 1) return fail(PD_EINVAL, "null argument");
     int threads = 128;
-    int grid = (int)std::min<int64_t>((B + threads - 1) / threads, 148 * 8);
+    int grid = (int)std::min<int64_t>((B + threads - 1) / threads, (int64_t)current_sm_count() * 8);
     count_errors_kernel<<<grid, threads, 0, (cudaStream_t)cuda_stream>>>(dev_decoded, dev_truth, B, len, dev_counters);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -734,7 +747,7 @@ int pd_sim_generate(pd_sim *S, double sigma, int64_t B, uint64_t seed, uint64_t 
     CUDA_TRY(cudaSetDevice(S->device));
     const int threads = 128, wpb = threads / 32;
     const size_t smem = (size_t)wpb * (S->dev.N / 32) * 4;
-    const int grid = (int)std::min<int64_t>((B + wpb - 1) / wpb, 148 * 16);
+    const int grid = (int)std::min<int64_t>((B + wpb - 1) / wpb, (int64_t)current_sm_count() * 16);
     sim_generate_kernel<<<grid, threads, smem, (cudaStream_t)cuda_stream>>>(S->dev, sigma, B, seed, first_frame, dev_msg, dev_out);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -760,7 +773,7 @@ int pd_sim_encode_device(pd_sim *S, int mode, const uint8_t *dev_in, int64_t B, 
     CUDA_TRY(cudaSetDevice(S->device));
     const int threads = 256, wpb = threads / 32;
     const size_t smem = (size_t)wpb * (S->dev.N / 32) * 4;
-    const int grid = (int)std::min<int64_t>((B + wpb - 1) / wpb, (int64_t)148 * 8);
+    const int grid = (int)std::min<int64_t>((B + wpb - 1) / wpb, (int64_t)current_sm_count() * 8);
     const int vec_ok = ((reinterpret_cast<uintptr_t>(dev_in) & 3) == 0 && (reinterpret_cast<uintptr_t>(dev_out) & 15) == 0) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (mode == PD_ENC_CRC) encode_kernel<ENC_CRC><<<grid, threads, smem, st>>>(S->dev, dev_in, dev_out, B, vec_ok);
