@@ -146,6 +146,7 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x) {
     return (x & 0xfu) | ((x >> 4) & 0xf0u) | ((x >> 8) & 0xf00u) | ((x >> 12) & 0xf000u);
 }
 
+// (register budget left to ptxas: 64 for the plain variants, 80 for the Fast ones; forcing 96 / 64 measured slower)
 template <int LOGL, bool CA, bool FAST>
 __global__ void __launch_bounds__(32)
 scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastParams fp, const void *__restrict__ in, int in_dtype,
