@@ -38,7 +38,10 @@ typedef enum pd_kind {
     PD_SCL_UNIFORM = 12,   /* SCLUniformQuantizedDecoder PD/src/SCLUniformQuantizedDecoder.cpp:43-184 */
     PD_SC_LLOYD = 13,      /* SCLloydQuantizedDecoder    PD/src/SCLloydQuantizedDecoder.cpp:22-101 */
     PD_SCL_LLOYD = 14,     /* SCLLloydQuantizedDecoder   PD/src/SCLLloydQuantizedDecoder.cpp:46-187 */
-    PD_KIND_COUNT = 15
+    /* blind-detection helpers of the reference's PolarEncoder/PolarBD package */
+    PD_BD_DMETRIC = 15,    /* DMetricCalculator          PolarEncoder/PolarBD/_cpp/src/DMetric.cpp:25-176 (Fast-SSC walk + metric) */
+    PD_BD_CASCL = 16,      /* PolarBD CASCLDecoder       PolarEncoder/PolarBD/_cpp/src/CASCLWithRNTI.cpp:74-252 (RNTI-scrambled CRC) */
+    PD_KIND_COUNT = 17
 } pd_kind;
 
 typedef enum pd_dtype {
@@ -156,6 +159,19 @@ void pd_sim_destroy(pd_sim *sim);
  * dev_out [B][N] uint8 symbols (quantizer given) or fp64 LLRs.  Asynchronous on cuda_stream. */
 int pd_sim_generate(pd_sim *sim, double sigma, int64_t B, uint64_t seed, uint64_t first_frame,
                     uint8_t *dev_msg, void *dev_out, void *cuda_stream);
+
+/* Blind-detection entry (kinds PD_BD_DMETRIC / PD_BD_CASCL; fp64 LLR input [B][N]).
+ *   PD_BD_DMETRIC: out_metric[b] = DMetricCalculator.calculate(llr_b) (DMetric.cpp:25-176); out_bits / out_pass unused (may be NULL).
+ *   PD_BD_CASCL:   CASCL::decode(llr_b, RNTI) (CASCLWithRNTI.cpp:74-252) -> out_bits [B][A], out_metric[b] = the PM it returns
+ *                  (PML[0], or PML[i] of the i-th candidate in sorted order that passed -- the reference indexes the
+ *                  unsorted array there, reproduced), out_pass[b] = isPass.  rnti: rnti_len 0/1 ints XORed onto the LAST
+ *                  rnti_len CRC bits, shared by all frames of the call (rnti_len <= crc_n; may be 0).
+ * pd_decode_bd takes host buffers; pd_decode_bd_device device buffers (rnti on the device too), asynchronous on cuda_stream.
+ * pd_decode / pd_decode_device also accept these kinds (plain Fast-SC bits / CA-SCL bits without RNTI). */
+int pd_decode_bd(pd_decoder *dec, const double *llr, int64_t B, const int32_t *rnti, int32_t rnti_len,
+                 uint8_t *out_bits, double *out_metric, uint8_t *out_pass);
+int pd_decode_bd_device(pd_decoder *dec, const double *dev_llr, int64_t B, const int32_t *dev_rnti, int32_t rnti_len,
+                        uint8_t *dev_bits, double *dev_metric, uint8_t *dev_pass, void *cuda_stream);
 
 /* Batched encoder side of the same object: what the drivers call on the PolarBDEnc package, which is
  * imported by all four drivers (mainFPDecoder.py:12-13,56-57,102-105) but absent from the reference tree.  Bits are one

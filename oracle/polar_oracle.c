@@ -25,7 +25,10 @@
 enum {
     PO_SC = 0, PO_FASTSC = 1, PO_SCL = 2, PO_FASTSCL = 3, PO_CASCL = 4,
     PO_SCLUT = 5, PO_FASTSCLUT = 6, PO_SCLLUT = 7, PO_FASTSCLLUT = 8, PO_CASCLLUT = 9, PO_CAFASTSCLLUT = 10,
-    PO_SC_UNIFORM = 11, PO_SCL_UNIFORM = 12, PO_SC_LLOYD = 13, PO_SCL_LLOYD = 14
+    PO_SC_UNIFORM = 11, PO_SCL_UNIFORM = 12, PO_SC_LLOYD = 13, PO_SCL_LLOYD = 14,
+    /* blind-detection helpers, BD/... = PolarEncoder/PolarBD/_cpp/... */
+    PO_BD_DMETRIC = 15,   /* DMetricCalculator::calculate   BD/src/DMetric.cpp:25-176 */
+    PO_BD_CASCL = 16      /* CASCL::decode(llr, RNTI)       BD/src/CASCLWithRNTI.cpp:74-252 */
 };
 
 typedef struct {
@@ -231,6 +234,7 @@ typedef struct {
     double **val;    /* [L][(n+1)*N] */
     uint8_t **uc;    /* [L][(n+1)*N] */
     double *PM;      /* [L] */
+    double dmetric;  /* PO_BD_DMETRIC accumulator */
     /* scratch for permutations */
     double **tval; uint8_t **tuc;
 } po_ctx;
@@ -313,12 +317,21 @@ static void leaf_action(po_ctx *x, int leaf) {
 static void fastsc_special(po_ctx *x, int type, int d, int node) {
     int N = x->c->N, temp = 1 << (x->n - d), base = temp * node;
     uint8_t *pu = x->uc[0] + (size_t)d * N + base;
-    if (type == 0) { memset(pu, 0, (size_t)temp); return; }
+    if (type == 0) {
+        memset(pu, 0, (size_t)temp);
+        if (x->c->kind == PO_BD_DMETRIC) {   /* BD/src/DMetric.cpp:56-61 */
+            double tmp = 0;
+            for (int i = 0; i < temp; ++i) tmp += elem_llr(x, 0, d, base + i);
+            x->dmetric += tmp / temp;
+        }
+        return;
+    }
     if (type == 1) { for (int i = 0; i < temp; ++i) pu[i] = (uint8_t)(elem_llr(x, 0, d, base + i) <= 0); return; }
     if (type == 2) {
         double S = 0;
         for (int i = 0; i < temp; ++i) S += elem_llr(x, 0, d, base + i);
         memset(pu, (uint8_t)(S <= 0), (size_t)temp);
+        if (x->c->kind == PO_BD_DMETRIC) x->dmetric += fabs(S) / temp;   /* BD/src/DMetric.cpp:87-93 */
         return;
     }
     /* SPC: Wagner, flip the FIRST arg-min |llr| when parity is odd */
@@ -467,20 +480,22 @@ static const int32_t CRC24_LOC[13] = {24, 23, 21, 20, 17, 15, 13, 12, 8, 4, 2, 1
 
 /* in: int32 [B][N] for LUT kinds, double [B][N] otherwise.  out: uint8 [B][Kout], Kout = A for CA kinds else K.
  * pm_out (optional): double [B][L] final path metrics in slot order; winner_out (optional): int32 [B].   */
-int po_decode(const po_config *c, const void *in, int64_t B, uint8_t *out, double *pm_out, int32_t *winner_out) {
+static int decode_impl(const po_config *c, const void *in, int64_t B, uint8_t *out, double *pm_out, int32_t *winner_out,
+                       const int32_t *rnti, int rnti_len, double *bd_metric, uint8_t *bd_pass) {
     po_ctx x; memset(&x, 0, sizeof x);
     x.c = c;
     int N = c->N, n = (int)log2f((float)N), k = c->kind;
     x.n = n;
     x.lut = (k >= PO_SCLUT && k <= PO_CAFASTSCLLUT);
     x.list = (k == PO_SCL || k == PO_FASTSCL || k == PO_CASCL || k == PO_SCLLUT || k == PO_FASTSCLLUT ||
-              k == PO_CASCLLUT || k == PO_CAFASTSCLLUT || k == PO_SCL_UNIFORM || k == PO_SCL_LLOYD);
-    x.fast = (k == PO_FASTSC || k == PO_FASTSCL || k == PO_FASTSCLUT || k == PO_FASTSCLLUT || k == PO_CAFASTSCLLUT);
-    x.spc = (k == PO_FASTSC || k == PO_FASTSCLUT);  /* list variants expand SPC nodes */
-    x.ca = (k == PO_CASCL || k == PO_CASCLLUT || k == PO_CAFASTSCLLUT);
+              k == PO_CASCLLUT || k == PO_CAFASTSCLLUT || k == PO_SCL_UNIFORM || k == PO_SCL_LLOYD || k == PO_BD_CASCL);
+    x.fast = (k == PO_FASTSC || k == PO_FASTSCL || k == PO_FASTSCLUT || k == PO_FASTSCLLUT || k == PO_CAFASTSCLLUT || k == PO_BD_DMETRIC);
+    x.spc = (k == PO_FASTSC || k == PO_FASTSCLUT || k == PO_BD_DMETRIC);  /* list variants expand SPC nodes */
+    x.ca = (k == PO_CASCL || k == PO_CASCLLUT || k == PO_CAFASTSCLLUT || k == PO_BD_CASCL);
     x.quant = (k == PO_SC_UNIFORM || k == PO_SCL_UNIFORM) ? 1 : (k == PO_SC_LLOYD || k == PO_SCL_LLOYD) ? 2 : 0;
     /* PD/include/SCLDecoder.h:8 (1e300) vs SCLLUTDecoder.h:16, FastSCLDecoder.h:7, FastSCLLUTDecoder.h:16 (+inf) */
     x.pm_init = (k == PO_SCL || k == PO_CASCL || k == PO_SCL_UNIFORM || k == PO_SCL_LLOYD) ? 1e300 : INFINITY;
+    if (k == PO_BD_CASCL) x.pm_init = 1e30;   /* BD/src/CASCLWithRNTI.cpp:82 */
     x.L = x.list ? c->L : 1;
     int L = x.L, Kout = x.ca ? c->A : c->K;
     size_t sz = (size_t)(n + 1) * N;
@@ -503,8 +518,10 @@ int po_decode(const po_config *c, const void *in, int64_t B, uint8_t *out, doubl
                 x.val[i][j] = x.lut ? (double)((const int32_t *)in)[b * N + j] : ((const double *)in)[b * N + j];
             x.PM[i] = (i == 0) ? 0.0 : x.pm_init;
         }
+        x.dmetric = 0;
         visit(&x, 0, 0);
-        int winner = 0;
+        int winner = 0, passed = 0;
+        double ret_pm = x.PM[0];   /* BD/src/CASCLWithRNTI.cpp:205 */
         if (x.list) {
             if (!x.ca) {
                 for (int i = 1; i < L; ++i) if (x.PM[i] < x.PM[winner]) winner = i;   /* std::min_element: first minimum */
@@ -512,9 +529,10 @@ int po_decode(const po_config *c, const void *in, int64_t B, uint8_t *out, doubl
                 for (int i = 0; i < L; ++i) order[i] = i;
                 po_std_sort_idx(order, L, x.PM);
                 winner = order[0];
-                const int32_t *poly = (k == PO_CASCL) ? c->crc_p : crc24;
-                int crc_n = (k == PO_CASCL) ? c->crc_n : 24;
-                int ncheck = (k == PO_CASCL) ? c->crc_n : c->K - c->A;    /* CASCLDecoder.cpp:222 vs CASCLLUTDecoder.cpp:280 */
+                const int own = (k == PO_CASCL || k == PO_BD_CASCL);
+                const int32_t *poly = own ? c->crc_p : crc24;
+                int crc_n = own ? c->crc_n : 24;
+                int ncheck = own ? c->crc_n : c->K - c->A;    /* CASCLDecoder.cpp:222 vs CASCLLUTDecoder.cpp:280 */
                 for (int t = 0; t < L; ++t) {
                     int cand = order[t], cnt = 0;
                     if (x.fast) {   /* CAFastSCLLUTDecoder.cpp:396-415: re-encode each candidate first */
@@ -527,12 +545,17 @@ int po_decode(const po_config *c, const void *in, int64_t B, uint8_t *out, doubl
                         for (int i = 0; i < N; ++i) if (c->frozen[i] == 0) info[cnt++] = x.uc[cand][(size_t)n * N + i];
                     }
                     p_crc(info, c->A, poly, crc_n, chk);
+                    for (int l = 0; l < rnti_len; ++l)   /* BD/src/CASCLWithRNTI.cpp:222-224 */
+                        chk[l + crc_n - rnti_len] = (uint8_t)((chk[l + crc_n - rnti_len] + rnti[l]) % 2);
                     int pass = 1;
                     for (int j = 0; j < ncheck; ++j) if (chk[j] != info[c->A + j]) { pass = 0; break; }
-                    if (pass) { winner = cand; break; }
+                    if (pass) { winner = cand; passed = 1; ret_pm = x.PM[t]; break; }   /* :236 PM = PML[i], the slot, not the candidate */
                 }
             }
         }
+        if (bd_metric) bd_metric[b] = (k == PO_BD_DMETRIC) ? x.dmetric : ret_pm;
+        if (bd_pass) bd_pass[b] = (uint8_t)passed;
+        if (!out) continue;
         uint8_t *o = out + b * Kout;
         int cnt = 0;
         if (x.fast) { /* re-encode the root codeword estimate: PD/src/FastSCLUT.cpp:186-205 */
@@ -551,4 +574,13 @@ int po_decode(const po_config *c, const void *in, int64_t B, uint8_t *out, doubl
     free(x.val); free(x.tval); free(x.uc); free(x.tuc); free(x.PM);
     free(xw); free(info); free(chk); free(order);
     return 0;
+}
+
+int po_decode(const po_config *c, const void *in, int64_t B, uint8_t *out, double *pm_out, int32_t *winner_out) {
+    return decode_impl(c, in, B, out, pm_out, winner_out, NULL, 0, NULL, NULL);
+}
+/* PO_BD_DMETRIC: metric[b] = the D-metric, out may be NULL.  PO_BD_CASCL: out [B][A], metric[b] = returned PM, pass[b]. */
+int po_decode_bd(const po_config *c, const double *in, int64_t B, const int32_t *rnti, int32_t rnti_len,
+                 uint8_t *out, double *metric, uint8_t *pass) {
+    return decode_impl(c, in, B, out, NULL, NULL, rnti, rnti_len, metric, pass);
 }

@@ -23,9 +23,11 @@ KINDS = {
     "CASCLLUTDecoder": 9, "CAFastSCLLUTDecoder": 10,
     "SCUniformQuantizedDecoder": 11, "SCLUniformQuantizedDecoder": 12,
     "SCLloydQuantizedDecoder": 13, "SCLLloydQuantizedDecoder": 14,
+    # blind-detection helpers of PolarEncoder/PolarBD (module libPolarBD: DMetricCalculator, CASCLDecoder)
+    "BDDMetricCalculator": 15, "BDCASCLDecoder": 16,
 }
 LUT_KINDS = {5, 6, 7, 8, 9, 10}
-CA_KINDS = {4, 9, 10}
+CA_KINDS = {4, 9, 10, 16}
 
 
 class _Cfg(C.Structure):
@@ -64,6 +66,8 @@ def lib():
         _lib.po_crc_attach.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib.po_polar_encode.restype = None
         _lib.po_polar_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.po_decode_bd.restype = C.c_int
+        _lib.po_decode_bd.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.po_std_sort_idx.restype = None
         _lib.po_std_sort_idx.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     return _lib
@@ -158,7 +162,7 @@ class OracleDecoder:
             cfg.nb, cfg.nr = bf.shape[1], rf.shape[1]
         self.cfg = cfg
         self.kout = self.A if self.kind in CA_KINDS else self.K
-        self.list = self.kind in (2, 3, 4, 7, 8, 9, 10, 12, 14)
+        self.list = self.kind in (2, 3, 4, 7, 8, 9, 10, 12, 14, 16)
 
     def decode(self, x, return_pm=False):
         x = np.asarray(x)
@@ -176,7 +180,48 @@ class OracleDecoder:
         return (res, pm, win) if return_pm else res
 
 
+    def decode_bd(self, x, rnti=None):
+        """BDDMetricCalculator: -> metric (B,) float64.  BDCASCLDecoder: -> (bits (B,A), PM (B,), isPass (B,) bool)."""
+        xb = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=np.float64)))
+        B = xb.shape[0]
+        metric = np.empty(B, np.float64)
+        if self.kind == KINDS["BDDMetricCalculator"]:
+            rc = lib().po_decode_bd(C.byref(self.cfg), xb.ctypes.data, B, None, 0, None, metric.ctypes.data, None)
+            assert rc == 0
+            return metric
+        r = np.ascontiguousarray(rnti if rnti is not None else [], dtype=np.int32)
+        bits = np.empty((B, self.kout), np.uint8)
+        ok = np.empty(B, np.uint8)
+        rc = lib().po_decode_bd(C.byref(self.cfg), xb.ctypes.data, B, r.ctypes.data if r.size else None, r.size,
+                                bits.ctypes.data, metric.ctypes.data, ok.ctypes.data)
+        assert rc == 0
+        return bits, metric, ok.astype(bool)
+
+
 # ---------------------------------------------------------------------------------------------------
+def bd_ref_path():
+    return os.path.join(HERE, "_ref", "libPolarBD" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+_bd_mod = None
+
+
+def load_bd_reference(reference_root="/root/reference"):
+    """oracle/_ref/libPolarBD*.so = the reference's PolarEncoder/PolarBD module compiled unmodified (built on demand where
+    the reference sources exist); None otherwise."""
+    global _bd_mod
+    if _bd_mod is None:
+        p = bd_ref_path()
+        if not os.path.exists(p) and os.path.isdir(reference_root):
+            subprocess.check_call(["make", "-C", HERE, "ref_bd", f"REFERENCE={reference_root}"], stdout=subprocess.DEVNULL)
+        if not os.path.exists(p):
+            return None
+        spec = importlib.util.spec_from_file_location("libPolarBD", p)
+        _bd_mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_bd_mod)
+    return _bd_mod
+
+
 def ref_path():
     return os.path.join(HERE, "_ref", "_libPolarDecoder" + sysconfig.get_config_var("EXT_SUFFIX"))
 

@@ -32,6 +32,9 @@ DECODER_CLASSES = (
 for _n in DECODER_CLASSES:
     globals()[_n] = getattr(_libPolarDecoder, _n)
 del _n
+# blind-detection helpers of the reference's PolarEncoder/PolarBD package
+BDDMetricCalculator = _libPolarDecoder.BDDMetricCalculator
+BDCASCLDecoder = _libPolarDecoder.BDCASCLDecoder
 
 LIB_PATH = _os.path.join(_HERE, "libpolar_b200.so")
 
@@ -45,4 +48,4 @@ def install_reference_import_paths():
     return PolarDecoder
 
 
-__all__ = list(DECODER_CLASSES) + ["install_reference_import_paths", "LIB_PATH"]
+__all__ = list(DECODER_CLASSES) + ["BDDMetricCalculator", "BDCASCLDecoder", "install_reference_import_paths", "LIB_PATH"]

@@ -62,12 +62,12 @@ int fail(int code, const char *fmt, ...) {
 bool is_lut(int k) { return k >= PD_SCLUT && k <= PD_CAFASTSCLLUT; }
 bool is_list(int k) {
     return k == PD_SCL || k == PD_FASTSCL || k == PD_CASCL || k == PD_SCLLUT || k == PD_FASTSCLLUT ||
-           k == PD_CASCLLUT || k == PD_CAFASTSCLLUT || k == PD_SCL_UNIFORM || k == PD_SCL_LLOYD;
+           k == PD_CASCLLUT || k == PD_CAFASTSCLLUT || k == PD_SCL_UNIFORM || k == PD_SCL_LLOYD || k == PD_BD_CASCL;
 }
 bool is_fast(int k) {
-    return k == PD_FASTSC || k == PD_FASTSCL || k == PD_FASTSCLUT || k == PD_FASTSCLLUT || k == PD_CAFASTSCLLUT;
+    return k == PD_FASTSC || k == PD_FASTSCL || k == PD_FASTSCLUT || k == PD_FASTSCLLUT || k == PD_CAFASTSCLLUT || k == PD_BD_DMETRIC;
 }
-bool is_ca(int k) { return k == PD_CASCL || k == PD_CASCLLUT || k == PD_CAFASTSCLLUT; }
+bool is_ca(int k) { return k == PD_CASCL || k == PD_CASCLLUT || k == PD_CAFASTSCLLUT || k == PD_BD_CASCL; }
 int domain_of(int k) {
     if (is_lut(k)) return DOM_LUT;
     if (k == PD_SC_UNIFORM || k == PD_SCL_UNIFORM) return DOM_UNIFORM;
@@ -418,7 +418,7 @@ int pd_create(const pd_config *c, pd_decoder **out) {
     if (ca) {
         if (c->A < 1 || c->A > c->K) return fail(PD_EINVAL, "A=%d must be in [1,K]", c->A);
         std::vector<int> poly;
-        if (kind == PD_CASCL) {   // honours the ctor polynomial, compares crc_n bits (PD/src/CASCLDecoder.cpp:49-53,222)
+        if (kind == PD_CASCL || kind == PD_BD_CASCL) {   // honours the ctor polynomial, compares crc_n bits (PD/src/CASCLDecoder.cpp:49-53,222; CASCLWithRNTI.cpp:48-56,228-233)
             crc_n = c->crc_n;
             if (crc_n < 1 || crc_n > 32) return fail(PD_EINVAL, "crc_n=%d unsupported (1..32)", crc_n);
             poly.assign(crc_n + 1, 0);
@@ -455,6 +455,8 @@ int pd_create(const pd_config *c, pd_decoder **out) {
     d.Kout = ca ? c->A : c->K;
     d.domain = domain_of(kind); d.list = list; d.fast = fastk; d.ca = ca;
     d.pm_init = (kind == PD_SCL || kind == PD_CASCL || kind == PD_SCL_UNIFORM || kind == PD_SCL_LLOYD) ? 1e300 : std::numeric_limits<double>::infinity();
+    if (kind == PD_BD_CASCL) d.pm_init = 1e30;   // CASCLWithRNTI.cpp:82
+    d.bd = kind == PD_BD_DMETRIC ? 1 : kind == PD_BD_CASCL ? 2 : 0;
     d.crc_n = crc_n; d.crc_check = crc_check; d.crc_taps = taps;
 
     Builder b{c, N, n, kind};
@@ -583,6 +585,75 @@ int pd_check(pd_decoder *D, void *cuda_stream) {
         return fail(PD_ERANGE, "an input symbol is outside the root lookup table (valid: [0,%d) for the first half, [0,%d) for the second)", D->dev.root_qa, D->dev.root_qb);
     }
     return PD_OK;
+}
+
+// ---- blind-detection kinds ------------------------------------------------------------------------
+int pd_decode_bd_device(pd_decoder *D, const double *dev_llr, int64_t B, const int32_t *dev_rnti, int32_t rnti_len,
+                        uint8_t *dev_bits, double *dev_metric, uint8_t *dev_pass, void *cuda_stream) {
+    if (!D || (B > 0 && (!dev_llr || !dev_metric))) return fail(PD_EINVAL, "null argument");
+    if (D->dev.bd == 0) return fail(PD_EINVAL, "pd_decode_bd: the decoder is not a PD_BD_* kind");
+    if (D->dev.bd == 2) {
+        if (B > 0 && (!dev_bits || !dev_pass)) return fail(PD_EINVAL, "null argument");
+        if (rnti_len < 0 || rnti_len > D->dev.crc_n || (rnti_len > 0 && !dev_rnti)) return fail(PD_EINVAL, "RNTI length %d must be in [0,crc_n=%d]", rnti_len, D->dev.crc_n);
+    }
+    if (B <= 0) return PD_OK;
+    CUDA_TRY(cudaSetDevice(D->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const size_t need = ws_need(D, PD_F64, dev_llr, B);
+    if (need > D->ws_user_cap) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(D->ws_user);
+        D->ws_user = nullptr; D->ws_user_cap = 0;
+        CUDA_TRY(cudaMalloc((void **)&D->ws_user, need));
+        D->ws_user_cap = need;
+    }
+    // per-call pointers ride in the descriptor, which every launch copies by value
+    Dev &d = D->dev;
+    d.bd_rnti = dev_rnti; d.bd_rnti_len = d.bd == 2 ? rnti_len : 0; d.bd_metric = dev_metric; d.bd_pass = dev_pass;
+    const int rc = launch(D, dev_llr, PD_F64, B, d.bd == 2 ? dev_bits : nullptr, s, D->ws_user);
+    d.bd_rnti = nullptr; d.bd_rnti_len = 0; d.bd_metric = nullptr; d.bd_pass = nullptr;
+    return rc;
+}
+
+int pd_decode_bd(pd_decoder *D, const double *llr, int64_t B, const int32_t *rnti, int32_t rnti_len,
+                 uint8_t *out_bits, double *out_metric, uint8_t *out_pass) {
+    if (!D || (B > 0 && (!llr || !out_metric))) return fail(PD_EINVAL, "null argument");
+    if (D->dev.bd == 0) return fail(PD_EINVAL, "pd_decode_bd: the decoder is not a PD_BD_* kind");
+    const bool ca = D->dev.bd == 2;
+    if (ca && B > 0 && (!out_bits || !out_pass)) return fail(PD_EINVAL, "null argument");
+    if (ca && (rnti_len < 0 || rnti_len > D->dev.crc_n || (rnti_len > 0 && !rnti))) return fail(PD_EINVAL, "RNTI length %d must be in [0,crc_n=%d]", rnti_len, D->dev.crc_n);
+    if (B <= 0) return PD_OK;
+    CUDA_TRY(cudaSetDevice(D->device));
+    const size_t N = D->dev.N, Ko = D->dev.Kout;
+    const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(1024, (int64_t)((32u << 20) / (N * 8))));
+    double *d_in = nullptr, *d_metric = nullptr;
+    uint8_t *d_bits = nullptr, *d_pass = nullptr;
+    int32_t *d_rnti = nullptr;
+    int rc = PD_OK;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_metric); cudaFree(d_bits); cudaFree(d_pass); cudaFree(d_rnti); };
+    if (cudaMalloc((void **)&d_in, (size_t)chunk * N * 8) != cudaSuccess || cudaMalloc((void **)&d_metric, (size_t)chunk * 8) != cudaSuccess ||
+        cudaMalloc((void **)&d_bits, std::max<size_t>((size_t)chunk * Ko, 16)) != cudaSuccess || cudaMalloc((void **)&d_pass, (size_t)chunk) != cudaSuccess ||
+        cudaMalloc((void **)&d_rnti, std::max<size_t>((size_t)rnti_len * 4, 16)) != cudaSuccess) {
+        cleanup();
+        cudaGetLastError();
+        return fail(PD_ENOMEM, "cudaMalloc failed");
+    }
+    cudaStream_t s = nullptr;
+    if (ca && rnti_len > 0 && cudaMemcpyAsync(d_rnti, rnti, (size_t)rnti_len * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) rc = fail(PD_ECUDA, "H2D copy failed");
+    for (int64_t f0 = 0; f0 < B && rc == PD_OK; f0 += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, B - f0);
+        if (cudaMemcpyAsync(d_in, llr + (size_t)f0 * N, (size_t)nb * N * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = fail(PD_ECUDA, "H2D copy failed"); break; }
+        if ((rc = pd_decode_bd_device(D, d_in, nb, d_rnti, rnti_len, d_bits, d_metric, d_pass, s))) break;
+        bool ok = cudaMemcpyAsync(out_metric + f0, d_metric, (size_t)nb * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+        if (ca) {
+            ok = ok && cudaMemcpyAsync(out_bits + (size_t)f0 * Ko, d_bits, (size_t)nb * Ko, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(out_pass + f0, d_pass, (size_t)nb, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+        }
+        if (!ok) { rc = fail(PD_ECUDA, "D2H copy failed"); break; }
+        rc = pd_check(D, s);
+    }
+    cleanup();
+    return rc;
 }
 
 int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8_t *host_out) {

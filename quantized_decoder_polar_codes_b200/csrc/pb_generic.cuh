@@ -207,6 +207,8 @@ struct Ctl {
     uint8_t ptrU[kMaxL][kMaxLog + 2];
     int winner;
     int pass;
+    double dmetric;   // PD_BD_DMETRIC accumulator (DMetric.cpp:35,61,93)
+    double bd_pm;     // PD_BD_CASCL: the PM value the reference returns
 };
 
 template <bool WARP>
@@ -329,6 +331,7 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
 
         if (tid < L) {
             c.PM[tid] = (tid == 0) ? 0.0 : d.pm_init;
+            if (tid == 0) c.dmetric = 0.0;
             c.rowp[tid] = (uint8_t)tid;
             for (int lv = 0; lv < kMaxLog + 2; ++lv) { c.ptrV[tid][lv] = (uint8_t)tid; c.ptrU[tid][lv] = (uint8_t)tid; }
         }
@@ -435,6 +438,11 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
                         c.PM[tid] = pm;
                     }
                 }
+                if (!LIST && d.bd == 1 && tid == 0) {   // DMetric.cpp:56-61: DMetric += (sum of the node's LLRs) / temp
+                    double tmp = 0;
+                    for (int j = 0; j < temp; ++j) tmp += elem_llr(0, dd, node, j);
+                    c.dmetric += tmp / temp;
+                }
                 for (int it = tid; it < L * temp; it += nth) {
                     const int i = it / temp, j = it - i * temp;
                     result_ptr(i, dd, node)[j] = 0;
@@ -449,6 +457,7 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
                         double S = 0;
                         for (int j = 0; j < temp; ++j) S += elem_llr(0, dd, node, j);
                         c.dec[0] = (uint8_t)(S <= 0);
+                        if (d.bd == 1) c.dmetric += fabs(S) / temp;   // DMetric.cpp:87-93
                     }
                     gsync<WARP>();
                     for (int j = tid; j < temp; j += nth) result_ptr(0, dd, node)[j] = c.dec[0];
@@ -570,6 +579,7 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
             }
             c.winner = w;
             c.pass = 0;
+            c.bd_pm = LIST ? c.PM[0] : 0.0;   // CASCLWithRNTI.cpp:205: PM = PML[0]
         }
         gsync<WARP>();
         if (LIST && d.ca) {
@@ -588,9 +598,11 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
                     int ok = 1;
                     for (int k = 0; k < d.crc_check; ++k) {
                         uint32_t bit = (reg >> (d.crc_n - 1 - k)) & 1u;
+                        // CASCLWithRNTI.cpp:224-226: the RNTI is added onto the last RNTILength check bits
+                        if (d.bd_rnti_len > 0 && k >= d.crc_n - d.bd_rnti_len) bit ^= (uint32_t)(d.bd_rnti[k - (d.crc_n - d.bd_rnti_len)] & 1);
                         if (bit != (uint32_t)X[d.info_pos[d.A + k]]) { ok = 0; break; }
                     }
-                    if (ok) { c.winner = cand; c.pass = 1; }
+                    if (ok) { c.winner = cand; c.pass = 1; c.bd_pm = c.PM[t]; }   // :236 PM = PML[i] (slot i, not the candidate's)
                 }
                 gsync<WARP>();
                 if (c.pass) break;
@@ -599,7 +611,9 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
         } else {
             load_transform(c.winner);
         }
-        for (int k = tid; k < d.Kout; k += nth) out[(size_t)frame * d.Kout + k] = X[d.info_pos[k]];
+        if (out) for (int k = tid; k < d.Kout; k += nth) out[(size_t)frame * d.Kout + k] = X[d.info_pos[k]];
+        if (d.bd_metric && tid == 0) d.bd_metric[frame] = d.bd == 1 ? c.dmetric : c.bd_pm;
+        if (d.bd_pass && tid == 0) d.bd_pass[frame] = (uint8_t)c.pass;
         if (dbg_pm && tid < L) dbg_pm[(size_t)frame * L + tid] = LIST ? c.PM[tid] : 0.0;
         if (dbg_win && tid == 0) dbg_win[frame] = c.winner;
         gsync<WARP>();

@@ -53,6 +53,12 @@ struct Dev {
     uint32_t crc_taps;
     // generic-kernel workspace geometry
     int r1_tmax;  // largest R1 node in the schedule (list Fast kinds), 0 if none
+    // blind-detection kinds (PD_BD_*), per call: metric / pass outputs and the RNTI mask; all null otherwise
+    int bd;                    // 0 none, 1 D-metric (DMetric.cpp), 2 CA-SCL with RNTI (CASCLWithRNTI.cpp)
+    const int32_t *bd_rnti;
+    int bd_rnti_len;
+    double *bd_metric;         // [B]
+    uint8_t *bd_pass;          // [B]
 };
 
 }  // namespace pb

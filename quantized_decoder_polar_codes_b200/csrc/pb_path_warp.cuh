@@ -185,6 +185,7 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
             pu = __shfl_sync(kAll, pu, p);
         };
 
+        double dmetric = 0.0;   // PD_BD_DMETRIC accumulator (one frame per lane there)
         Step st_next = d.steps[0];
         for (int si = 0; si < d.n_steps; ++si) {
             const Step st = st_next;
@@ -288,6 +289,12 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
                 break;
             }
             case OP_R0: {
+                if (L == 1 && d.bd == 1) {   // DMetric.cpp:56-61: DMetric += (sum of the node's LLRs) / temp
+                    const T *src = level_ptr(dd, vslot(dd));
+                    double tmp = 0;
+                    for (int j = 0; j < temp; ++j) tmp += elem_llr(dd, node, src, j);
+                    dmetric += tmp / temp;
+                }
                 if (L > 1) {   // PD/src/FastSCLDecoder.cpp:124-136
                     const T *src = level_ptr(dd, vslot(dd));
                     for (int j = 0; j < temp; ++j) {
@@ -305,6 +312,7 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
                     double S = 0;
                     for (int j = 0; j < temp; ++j) S += elem_llr(dd, node, src, j);
                     fill = S <= 0 ? 0xffffffffu : 0u;
+                    if (d.bd == 1) dmetric += fabs(S) / temp;   // DMetric.cpp:87-93
                 } else {       // PD/src/FastSCLDecoder.cpp:208-251
                     double a0 = PM, a1 = PM;
                     for (int j = 0; j < temp; ++j) {
@@ -429,6 +437,8 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
         auto ubit = [&](int pos) -> uint32_t { return (SC[(pos >> 5) * FPW + grp] >> (pos & 31)) & 1u; };
 
         int winner = lane;
+        double bd_pm = 0.0;
+        bool bd_passed = false;
         if (L > 1) {
             __syncwarp();
             KS[lane] = PM;
@@ -448,6 +458,7 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
                 }
                 __syncwarp();
                 winner = gbase | ORD[gbase * 2];
+                bd_pm = KS[gbase];                       // CASCLWithRNTI.cpp:205: PM = PML[0]
                 bool decided = false;
                 for (int t = 0; t < L; ++t) {
                     const int cand = gbase | ORD[gbase * 2 + t];
@@ -463,11 +474,15 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
                             if (topb) reg ^= d.crc_taps;
                         }
                         pass = true;
-                        for (int k = 0; k < d.crc_check; ++k)
-                            if (((reg >> (d.crc_n - 1 - k)) & 1u) != ubit(d.info_pos[d.A + k])) { pass = false; break; }
+                        for (int k = 0; k < d.crc_check; ++k) {
+                            uint32_t bit = (reg >> (d.crc_n - 1 - k)) & 1u;
+                            // CASCLWithRNTI.cpp:224-226: the RNTI is added onto the last RNTILength check bits
+                            if (d.bd_rnti_len > 0 && k >= d.crc_n - d.bd_rnti_len) bit ^= (uint32_t)(d.bd_rnti[k - (d.crc_n - d.bd_rnti_len)] & 1);
+                            if (bit != ubit(d.info_pos[d.A + k])) { pass = false; break; }
+                        }
                     }
                     pass = __shfl_sync(kAll, (int)pass, gbase) != 0;
-                    if (pass && !decided) { winner = cand; decided = true; }
+                    if (pass && !decided) { winner = cand; decided = true; bd_passed = true; bd_pm = KS[gbase + t]; }   // :236 PM = PML[i]
                     if (__all_sync(kAll, decided)) break;
                 }
             }
@@ -476,8 +491,12 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
         {
             const long long frame = g * FPW + grp;
             if (frame < B) {
-                uint8_t *o = out + (size_t)frame * d.Kout;
-                for (int k = me; k < d.Kout; k += L) o[k] = (uint8_t)ubit(d.info_pos[k]);
+                if (out) {
+                    uint8_t *o = out + (size_t)frame * d.Kout;
+                    for (int k = me; k < d.Kout; k += L) o[k] = (uint8_t)ubit(d.info_pos[k]);
+                }
+                if (d.bd_metric && me == 0) d.bd_metric[frame] = d.bd == 1 ? dmetric : bd_pm;
+                if (d.bd_pass && me == 0) d.bd_pass[frame] = (uint8_t)bd_passed;
                 if (dbg_pm) dbg_pm[(size_t)frame * L + me] = L > 1 ? PM : 0.0;
                 if (dbg_win && me == 0) dbg_win[frame] = winner - gbase;
             }

@@ -202,6 +202,53 @@ public:
         return out;
     }
 
+    // shape handling shared by the blind-detection entries: (N,), (1,N) -> one frame; (B,N) -> batch
+    DArr llr_frames(const py::object &x, int64_t &B, bool &flat) const {
+        DArr arr = DArr::ensure(x);
+        if (!arr) throw py::value_error("expected a float array");
+        if (arr.ndim() == 1) {
+            if (arr.shape(0) < N_) throw py::value_error("need at least N values");
+            B = 1; flat = true;
+        } else if (arr.ndim() == 2 && arr.shape(1) == N_) {
+            B = arr.shape(0); flat = (B == 1);
+        } else {
+            throw py::value_error("expected shape (N,), (1,N) or (B,N)");
+        }
+        return arr;
+    }
+    // DMetricCalculator.calculate (PolarEncoder/PolarBD/_cpp/src/DMetric.cpp:25): float for one frame, (B,) for a batch
+    py::object bd_calculate(const py::object &x) {
+        int64_t B; bool flat;
+        DArr arr = llr_frames(x, B, flat);
+        py::array_t<double> metric((py::ssize_t)B);
+        int rc;
+        {
+            py::gil_scoped_release nogil;
+            rc = pd_decode_bd(dec_, arr.data(), B, nullptr, 0, nullptr, metric.mutable_data(), nullptr);
+        }
+        if (rc != PD_OK) raise_status(rc);
+        if (flat) return py::float_(metric.data()[0]);
+        return std::move(metric);
+    }
+    // PolarBD CASCL::decode(llr, RNTI) -> (bits, PM, isPass)  (CASCLWithRNTI.cpp:74,251)
+    py::tuple bd_decode(const py::object &x, const py::object &rnti) {
+        int64_t B; bool flat;
+        DArr arr = llr_frames(x, B, flat);
+        std::vector<int32_t> r = to_ivec(rnti);
+        const int ko = pd_out_len(dec_);
+        py::array_t<uint8_t> bits = flat ? py::array_t<uint8_t>(ko) : py::array_t<uint8_t>({(py::ssize_t)B, (py::ssize_t)ko});
+        py::array_t<double> pm((py::ssize_t)B);
+        py::array_t<uint8_t> pass((py::ssize_t)B);
+        int rc;
+        {
+            py::gil_scoped_release nogil;
+            rc = pd_decode_bd(dec_, arr.data(), B, r.data(), (int32_t)r.size(), bits.mutable_data(), pm.mutable_data(), pass.mutable_data());
+        }
+        if (rc != PD_OK) raise_status(rc);
+        if (flat) return py::make_tuple(bits, py::float_(pm.data()[0]), py::bool_(pass.data()[0] != 0));
+        return py::make_tuple(bits, pm, pass.attr("astype")("bool"));
+    }
+
     std::string kernel() const { return pd_kernel_name(dec_); }
     uintptr_t handle() const { return reinterpret_cast<uintptr_t>(dec_); }
 
@@ -313,5 +360,25 @@ PYBIND11_MODULE(_libPolarDecoder, m) {
         .def(py::init([](int N, int K, int L, py::object fb, py::object mb, py::object bf, py::object bg, py::object rf, py::object rg, int v, int device) {
                  MK(PD_SCL_LLOYD); self->init(PD_SCL_LLOYD, N, K, 0, L, fb, NONE, 0, NONE, NONE, NONE, NONE, NONE, NONE, v, bf, bg, rf, rg, device); return self; }),
              arg("N"), arg("K"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("boundaries_f"), arg("boundaries_g"), arg("reconstruction_f"), arg("reconstruction_g"), arg("v"), arg("device") = 0);
+    // Blind-detection helpers of PolarEncoder/PolarBD (module libPolarBD there; re-exported under the reference's names by
+    // quantized_decoder_polar_codes_b200/PolarBD):  py_DMetric.cpp:10-13, py_CASCLWithRNTI.cpp:8-11
+    {
+        py::class_<Cls<PD_BD_DMETRIC>> c(m, "BDDMetricCalculator", "DMetric Calculator with Fast-SSC");
+        c.def(py::init([](int N, int K, py::object fb, py::object mb, py::object nt, int device) {
+                  MK(PD_BD_DMETRIC); self->init(PD_BD_DMETRIC, N, K, 0, 1, fb, nt, 0, NONE, NONE, NONE, NONE, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+              arg("N"), arg("K"), arg("frozen_bits"), arg("message_bits"), arg("node_type"), arg("device") = 0);
+        c.def("calculate", &Decoder::bd_calculate, arg("llr"));
+        c.def_property_readonly("kernel", &Decoder::kernel);
+        c.def_property_readonly("_handle", &Decoder::handle);
+    }
+    {
+        py::class_<Cls<PD_BD_CASCL>> c(m, "BDCASCLDecoder", "CRC Aided Successive Cancellation List Decoder (RNTI-scrambled CRC)");
+        c.def(py::init([](int N, int K, int A, int L, py::object fb, py::object mb, int crc_n, py::object crc_p, int device) {
+                  MK(PD_BD_CASCL); self->init(PD_BD_CASCL, N, K, A, L, fb, NONE, crc_n, crc_p, NONE, NONE, NONE, NONE, NONE, 0, NONE, NONE, NONE, NONE, device); return self; }),
+              arg("N"), arg("K"), arg("A"), arg("L"), arg("frozen_bits"), arg("message_bits"), arg("crc_n"), arg("crc_p"), arg("device") = 0);
+        c.def("decode", &Decoder::bd_decode, arg("llr"), arg("RNTI"));
+        c.def_property_readonly("kernel", &Decoder::kernel);
+        c.def_property_readonly("_handle", &Decoder::handle);
+    }
 #undef MK
 }
