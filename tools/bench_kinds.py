@@ -76,6 +76,52 @@ def main():
         print(json.dumps({"shape": name, "class": kind, "kernel": dec.kernel, "frames": F, "ms": round(best, 3), "frames_per_s": fps,
                           "info_gbit_s": fps * a / 1e9, "alg_bytes_per_frame": bpf, "alg_GBps": fps * bpf / 1e9,
                           "hbm_frac_of_measured": fps * bpf / 1e9 / peak}), flush=True)
+    bench_bd(args, peak)
+
+
+def bench_bd(args, peak):
+    """The two blind-detection kinds (pd_decode_bd_device): D-metric N=1024 K=512, CA-SCL+RNTI N=512 A=100 L=8."""
+    import torch
+    import ctypes as C
+    import quantized_decoder_polar_codes_b200 as q
+    from quantized_decoder_polar_codes_b200 import capi
+    from quantized_decoder_polar_codes_b200 import simulation as sim
+    lib = capi.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(0)
+    for name, N, K, A, L, F in [("BD D-metric N=1024 K=512", 1024, 512, 0, 1, 1 << 18), ("BD CA-SCL+RNTI N=512 A=100 L=8", 512, 124, 100, 8, 1 << 16)]:
+        if args.only and args.only not in name:
+            continue
+        fm, mm = sim.frozen_mask(N, K)
+        if A:
+            dec = q.BDCASCLDecoder(N, K, A, L, fm, mm, 24, list(sim.CRC24_LOC))
+        else:
+            dec = q.BDDMetricCalculator(N, K, fm, mm, sim.identify_nodes(N, fm))
+        msg = rng.integers(0, 2, (2048, K), dtype=np.uint8)
+        llr = sim.awgn_llr(sim.polar_encode(msg, fm), sim.awgn_sigma(2.0, K / N), rng)
+        d_in = torch.from_numpy(np.tile(llr, (F // 2048, 1))).cuda()
+        d_bits = torch.empty((F, max(A, 1)), dtype=torch.uint8, device="cuda")
+        d_metric = torch.empty(F, dtype=torch.float64, device="cuda")
+        d_pass = torch.empty(F, dtype=torch.uint8, device="cuda")
+        d_rnti = torch.zeros(16, dtype=torch.int32, device="cuda")
+
+        def run():
+            capi.check(lib.pd_decode_bd_device(dec._handle, d_in.data_ptr(), F, d_rnti.data_ptr(), 16 if A else 0,
+                                               d_bits.data_ptr(), d_metric.data_ptr(), d_pass.data_ptr(), stream))
+        run()
+        capi.sync_check(dec, stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(args.reps):
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        fps = F / (best / 1e3)
+        bpf = 8 * N + (A + 9 if A else 8)
+        print(json.dumps({"shape": name, "kernel": dec.kernel, "frames": F, "ms": round(best, 3), "frames_per_s": fps,
+                          "alg_bytes_per_frame": bpf, "alg_GBps": fps * bpf / 1e9, "hbm_frac_of_measured": fps * bpf / 1e9 / peak}), flush=True)
 
 
 if __name__ == "__main__":
