@@ -201,7 +201,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def run_ours(args, rank, local_rank, world):
@@ -329,10 +329,29 @@ def run_ours(args, rank, local_rank, world):
                                         "sample": f"{args.ref_frames} frames per core ({wall:.1f} s), one pinned process per core, per-frame decode() calls of the compiled reference"}
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG is set): keep a private handle on the real stdout for the result and point fd 1 at stderr for everyone else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
 
 
 def main():
@@ -352,6 +371,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

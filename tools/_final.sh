@@ -1,0 +1,5 @@
+#!/bin/bash
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py > gpurun_out/bench_r1_g.json 2> gpurun_out/bench_r1_g.err; tail -2 gpurun_out/bench_r1_g.err; cat gpurun_out/bench_r1_g.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_g.json 2> gpurun_out/bench_ref_g.err; tail -2 gpurun_out/bench_ref_g.err; cat gpurun_out/bench_ref_g.json
