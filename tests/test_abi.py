@@ -103,3 +103,27 @@ def test_no_cpu_fallback_in_product_sources():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "polar_oracle" not in txt and "oracle/" not in txt.replace("oracle/_ref", ""), f
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = tmp_path / "sc_roundtrip"
+    pkg = os.path.join(ROOT, "quantized_decoder_polar_codes_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "sc_roundtrip.c"), "-L" + pkg, "-lpolar_b200", "-Wl,-rpath," + pkg, "-o", str(exe)])
+    return exe
+
+
+def test_plain_c_caller_builds_and_links(tmp_path):
+    """include/polar_b200.h is a C header and libpolar_b200.so a C-ABI library: a C99 program links against it."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    assert subprocess.check_output([str(exe), "--version"]).decode().startswith("polar_b200")
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_round_trip(tmp_path):
+    """examples/sc_roundtrip.c: encode (CRC + polar) -> noiseless channel -> SC and CA-SCL decode, all through the C ABI."""
+    import subprocess
+    out = subprocess.check_output([str(_build_c_example(tmp_path))]).decode()
+    assert out.startswith("ok: 1000 frames")
