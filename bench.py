@@ -317,6 +317,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "kernel_ms": kernel_ms, "bytes_per_frame": BYTES_PER_FRAME,
+                         "per": "decode call of one step = 4 scl_lut_warp launches overlapped on two internal streams; algorithmic bytes, kernel_ms and traffic all refer to that call",
                          "note": "HBM-nominal codec path; the kernel is SM-issue bound, not HBM bound (see DESIGN.md 4.1, profiles/)"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * N, "d2h_bytes_per_step": F * K},
             "gpu_launches": int(l_after - l_before),

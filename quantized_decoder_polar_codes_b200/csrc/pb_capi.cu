@@ -112,7 +112,11 @@ struct pd_decoder {
     size_t ws_user_cap = 0;
     StreamSlot slot[2];
     int64_t chunk_frames = 0;
+    // pd_decode, tiny calls (the reference drivers decode one frame per call): a mapped pinned staging area the kernel
+    // reads and writes directly -- no copy engine round trips
+    char *h_small = nullptr, *d_small = nullptr;
 };
+constexpr size_t kSmallIn = 64 << 10, kSmallOut = 16 << 10;   // bytes of input / output served by the mapped path
 
 namespace {
 
@@ -387,6 +391,7 @@ void pd_destroy(pd_decoder *D) {
     }
     cudaFree(D->ws_user);
     if (D->h_err) cudaFreeHost((void *)D->h_err);
+    if (D->h_small) cudaFreeHost(D->h_small);
     for (int i = 0; i < 2; ++i) { if (D->side[i]) { cudaStreamSynchronize(D->side[i]); cudaStreamDestroy(D->side[i]); } if (D->join_ev[i]) cudaEventDestroy(D->join_ev[i]); }
     if (D->fork_ev) cudaEventDestroy(D->fork_ev);
     for (void *p : D->allocs) cudaFree(p);
@@ -663,6 +668,23 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
     if (B <= 0) return PD_OK;
     CUDA_TRY(cudaSetDevice(D->device));
     const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
+    if (B * N * esz <= kSmallIn && B * Ko <= kSmallOut && !getenv("POLAR_B200_NO_MAPPED_IO")) {
+        StreamSlot &sl = D->slot[0];
+        if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!D->h_small) {
+            void *hp = nullptr, *dp = nullptr;
+            CUDA_TRY(cudaHostAlloc(&hp, kSmallIn + kSmallOut, cudaHostAllocMapped));
+            if (cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) { cudaFreeHost(hp); return fail(PD_ECUDA, "cudaHostGetDevicePointer failed"); }
+            D->h_small = (char *)hp; D->d_small = (char *)dp;
+        }
+        const size_t wsn = std::max(ws_need(D, in_dtype, D->d_small, B), (size_t)16);
+        if (sl.ws_cap < wsn) { cudaFree(sl.ws); sl.ws = nullptr; sl.ws_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.ws, wsn)); sl.ws_cap = wsn; }
+        memcpy(D->h_small, host_in, (size_t)B * N * esz);
+        if ((rc = launch(D, D->d_small, in_dtype, B, reinterpret_cast<uint8_t *>(D->d_small + kSmallIn), sl.stream, sl.ws))) return rc;
+        if ((rc = pd_check(D, sl.stream))) return rc;
+        memcpy(host_out, D->h_small + kSmallIn, (size_t)B * Ko);
+        return PD_OK;
+    }
     // pipeline chunk: ~16 MB of input (two streams alternate, so copies of one chunk hide behind the kernel of the other
     // and the tail of one persistent launch overlaps the head of the next)
     const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(8192, (int64_t)((16u << 20) / (N * esz))));
