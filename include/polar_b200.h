@@ -187,6 +187,16 @@ int pd_decode_bd_device(pd_decoder *dec, const double *dev_llr, int64_t B, const
 int pd_sim_encode(pd_sim *sim, int mode, const uint8_t *in, int64_t B, uint8_t *out);
 int pd_sim_encode_device(pd_sim *sim, int mode, const uint8_t *dev_in, int64_t B, uint8_t *dev_out, void *cuda_stream);
 
+/* Lookup-table design: the minimum-distortion quantizer the reference's LLR-domain generator runs on every
+ * tree node -- LLRQuantizer.find_OptLS_quantizer(density, quanta, M, K) (QLLRDensityEvolution_MinDistortion.py:107-108;
+ * C++ on OpenCV in Quantizers/.../LLRQuantizer.cpp:67-164, numpy restatement MinDistortionQuantizer.py:28-99, which this
+ * follows bit for bit) -- for P independent problems at once, one CTA each.  Problem p: M[p] symbols (K < M[p] <= 1024) with
+ * probabilities density[p*stride + i] and values quanta[p*stride + i], STRICTLY ASCENDING in i (np.unique output, as the
+ * generator passes them).  Out: density / quanta of the K merged symbols [P][K], lut[p*stride + i] = merged symbol of i.
+ * Host buffers; runs on `device`. */
+int pd_optls_quantize(const double *density, const double *quanta, const int32_t *M, int64_t stride, int32_t P, int32_t K,
+                      double *out_density, double *out_quanta, int32_t *out_lut, int32_t device);
+
 /* Kernels launched by this library on the calling process so far (bench.py reports it as gpu_launches). */
 int64_t pd_launch_count(void);
 /* Name of the kernel variant pd_decode* uses for this decoder ("generic", "scl_lut_warp", ...). */

@@ -584,3 +584,83 @@ int po_decode_bd(const po_config *c, const double *in, int64_t B, const int32_t 
                  uint8_t *out, double *metric, uint8_t *pass) {
     return decode_impl(c, in, B, out, NULL, NULL, rnti, rnti_len, metric, pass);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Lookup-table design: the minimum-distortion quantizer the LLR-domain generator calls on every
+ * tree node, LLRQuantizer.find_OptLS_quantizer (QuantizeDensityEvolution/QLLRDensityEvolution_MinDistortion.py:107-108).
+ * The generator of record is C++ on OpenCV (Quantizers/quantizers/_cpp/LLRQuantizer/LLRQuantizer.cpp, cannot be built
+ * here); the reference also ships a numpy restatement, QuantizeDensityEvolution/MinDistortionQuantizer.py:28-99 = MDQ,
+ * which is what this follows INCLUDING numpy's summation order (np.sum of a contiguous float64 array = the pairwise
+ * routine below; checked against numpy 2.3 in tests/test_lutgen.py and pinned by golden vectors made with MDQ itself).
+ * ------------------------------------------------------------------------------------------------ */
+static double np_pairwise(const double *a, int n) {
+    if (n < 8) {
+        double r = 0.;
+        for (int i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        int i;
+        for (i = 0; i < 8; ++i) r[i] = a[i];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise(a, n2) + np_pairwise(a + n2, n - n2);
+}
+double po_np_sum(const double *a, int n) { return np_pairwise(a, n); }
+
+/* MDQ:3-7 compute_partial_quantization_noise on the slice [lo,hi) */
+static double optls_noise(const double *d, const double *q, int lo, int hi, double *tmp) {
+    int n = hi - lo;
+    for (int i = 0; i < n; ++i) tmp[i] = d[lo + i] * q[lo + i];
+    double nq = np_pairwise(tmp, n) / np_pairwise(d + lo, n);
+    for (int i = 0; i < n; ++i) { double e = q[lo + i] - nq; tmp[i] = (e * e) * d[lo + i]; }
+    return np_pairwise(tmp, n);
+}
+/* density / quanta: M entries sorted by ascending quanta (the generator passes np.unique output, so MDQ's argsort is
+ * the identity), M > K.  out_density[K], out_quanta[K], out_lut[M]. */
+int po_optls_quantize(const double *d, const double *q, int M, int K, double *out_density, double *out_quanta, int32_t *out_lut) {
+    if (M <= K || K < 2) return 1;
+    const int W = M - K + 1;
+    double *T = (double *)calloc((size_t)M * (M + 1), sizeof(double)), *tmp = (double *)malloc(sizeof(double) * M);
+    double *state = (double *)calloc((size_t)W * (K + 1), sizeof(double));
+    int *lm = (int *)calloc((size_t)W * (K + 1), sizeof(int)), *Az = (int *)calloc((size_t)K + 1, sizeof(int));
+    for (int ap = 0; ap < M; ++ap) {                       /* MDQ:20-24 */
+        int max_a = ap + W < M ? ap + W : M;
+        for (int a = ap + 1; a <= max_a; ++a) T[(size_t)ap * (M + 1) + a] = optls_noise(d, q, ap, a, tmp);
+    }
+    for (int i = 0; i < W; ++i) state[(size_t)i * (K + 1) + 1] = T[1 + i];   /* MDQ:44 */
+    for (int z = 2; z <= K; ++z) {                        /* MDQ:50-77: np.argmin / np.min = first minimum */
+        int a_lo = z < K ? z : M, a_hi = z < K ? z + M - K : M;
+        for (int a = a_lo; a <= a_hi; ++a) {
+            int row = z < K ? a - z : W - 1, best_ap = z - 1;
+            double best = state[(size_t)0 * (K + 1) + (z - 1)] + T[(size_t)(z - 1) * (M + 1) + a];
+            for (int ap = z; ap <= a - 1; ++ap) {
+                double v = state[(size_t)(ap - (z - 1)) * (K + 1) + (z - 1)] + T[(size_t)ap * (M + 1) + a];
+                if (v < best) { best = v; best_ap = ap; }
+            }
+            state[(size_t)row * (K + 1) + z] = best;
+            lm[(size_t)row * (K + 1) + z] = best_ap;
+        }
+    }
+    Az[K] = M;                                             /* MDQ:80-84 backward tracing */
+    int opt = lm[(size_t)(W - 1) * (K + 1) + K];
+    Az[K - 1] = opt;
+    for (int z = K - 1; z >= 2; --z) { opt = lm[(size_t)(opt - z) * (K + 1) + z]; Az[z - 1] = opt; }
+    for (int i = 0; i < K; ++i) {                          /* MDQ:87-96 */
+        int b = Az[i], e = Az[i + 1];
+        for (int j = b; j < e; ++j) { out_lut[j] = i; tmp[j - b] = q[j] * d[j]; }
+        double sd = np_pairwise(d + b, e - b);
+        out_quanta[i] = np_pairwise(tmp, e - b) / sd;
+        out_density[i] = sd;
+    }
+    free(T); free(tmp); free(state); free(lm); free(Az);
+    return 0;
+}
+

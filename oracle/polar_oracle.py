@@ -68,6 +68,10 @@ def lib():
         _lib.po_polar_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib.po_decode_bd.restype = C.c_int
         _lib.po_decode_bd.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.po_np_sum.restype = C.c_double
+        _lib.po_np_sum.argtypes = [C.c_void_p, C.c_int]
+        _lib.po_optls_quantize.restype = C.c_int
+        _lib.po_optls_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.po_std_sort_idx.restype = None
         _lib.po_std_sort_idx.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     return _lib
@@ -270,3 +274,15 @@ def polar_encode(word, msg_positions, N):
     out = np.empty((w.shape[0], int(N)), np.uint8)
     lib().po_polar_encode(w.ctypes.data, w.shape[0], w.shape[1], pos.ctypes.data, int(N), out.ctypes.data)
     return out
+
+
+def optls_quantize(density, quanta, K):
+    """Minimum-distortion quantizer of the LLR-domain table generator (MinDistortionQuantizer.py:28-99) for inputs sorted by
+    ascending quanta, M > K.  -> (density[K], quanta[K], lut[M] int32)."""
+    d = np.ascontiguousarray(density, dtype=np.float64)
+    q = np.ascontiguousarray(quanta, dtype=np.float64)
+    assert d.ndim == 1 and d.shape == q.shape and np.all(np.diff(q) > 0)
+    od, oq, lut = np.empty(K), np.empty(K), np.empty(d.size, np.int32)
+    rc = lib().po_optls_quantize(d.ctypes.data, q.ctypes.data, d.size, int(K), od.ctypes.data, oq.ctypes.data, lut.ctypes.data)
+    assert rc == 0
+    return od, oq, lut

@@ -23,6 +23,7 @@
 #include "pb_path_warp.cuh"
 #include "pb_sim.cuh"
 #include "pb_enc.cuh"
+#include "pb_lutgen.cuh"
 
 using namespace pb;
 
@@ -900,6 +901,57 @@ int pd_sim_encode(pd_sim *S, int mode, const uint8_t *in, int64_t B, uint8_t *ou
     }
     cudaFree(d_in);
     cudaFree(d_out);
+    return rc;
+}
+
+// ---- lookup-table design: batched minimum-distortion quantizer -----------------------------------------
+int pd_optls_quantize(const double *density, const double *quanta, const int32_t *M, int64_t stride, int32_t P, int32_t K,
+                      double *out_density, double *out_quanta, int32_t *out_lut, int32_t device) {
+    if (P <= 0) return PD_OK;
+    if (!density || !quanta || !M || !out_density || !out_quanta || !out_lut) return fail(PD_EINVAL, "null argument");
+    if (K < 2 || K > 64) return fail(PD_EINVAL, "K=%d must be in [2,64]", K);
+    int maxM = 0;
+    for (int p = 0; p < P; ++p) {
+        if (M[p] <= K || M[p] > kOptlsMaxM || M[p] > stride) return fail(PD_EINVAL, "problem %d: M=%d must be in (K,%d] and <= stride", p, M[p], kOptlsMaxM);
+        for (int i = 1; i < M[p]; ++i)
+            if (!(quanta[(size_t)p * stride + i] > quanta[(size_t)p * stride + i - 1])) return fail(PD_EINVAL, "problem %d: quanta must be strictly ascending (pass np.unique output)", p);
+        maxM = std::max(maxM, M[p]);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PD_ECUDA, "no CUDA device: libpolar_b200 has no CPU path");
+    if (device < 0 || device >= ndev) return fail(PD_EINVAL, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    const int W = maxM - K + 1;
+    const long long t_stride = (long long)maxM * W, lm_stride = (long long)(K + 1) * W;
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(P, (256ll << 20) / (t_stride * 8)));   // <= 256 MiB of tables in flight
+    double *d_d = nullptr, *d_q = nullptr, *d_od = nullptr, *d_oq = nullptr, *d_T = nullptr;
+    int32_t *d_M = nullptr, *d_lut = nullptr, *d_lm = nullptr;
+    auto cleanup = [&]() { cudaFree(d_d); cudaFree(d_q); cudaFree(d_od); cudaFree(d_oq); cudaFree(d_T); cudaFree(d_M); cudaFree(d_lut); cudaFree(d_lm); };
+    if (cudaMalloc((void **)&d_d, (size_t)chunk * stride * 8) != cudaSuccess || cudaMalloc((void **)&d_q, (size_t)chunk * stride * 8) != cudaSuccess ||
+        cudaMalloc((void **)&d_od, (size_t)chunk * K * 8) != cudaSuccess || cudaMalloc((void **)&d_oq, (size_t)chunk * K * 8) != cudaSuccess ||
+        cudaMalloc((void **)&d_T, (size_t)chunk * t_stride * 8) != cudaSuccess || cudaMalloc((void **)&d_M, (size_t)chunk * 4) != cudaSuccess ||
+        cudaMalloc((void **)&d_lut, (size_t)chunk * stride * 4) != cudaSuccess || cudaMalloc((void **)&d_lm, (size_t)chunk * lm_stride * 4) != cudaSuccess) {
+        cleanup();
+        cudaGetLastError();
+        return fail(PD_ENOMEM, "cudaMalloc failed");
+    }
+    int rc = PD_OK;
+    const size_t smem = (size_t)(2 * maxM + 2 * W) * sizeof(double);
+    for (int p0 = 0; p0 < P && rc == PD_OK; p0 += chunk) {
+        const int np = std::min(chunk, P - p0);
+        bool ok = cudaMemcpy(d_d, density + (size_t)p0 * stride, (size_t)np * stride * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(d_q, quanta + (size_t)p0 * stride, (size_t)np * stride * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(d_M, M + p0, (size_t)np * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) { rc = fail(PD_ECUDA, "H2D copy failed"); break; }
+        optls_kernel<<<np, 256, smem>>>(d_d, d_q, d_M, stride, K, d_od, d_oq, d_lut, d_T, d_lm, t_stride, lm_stride);
+        g_launches++;
+        ok = cudaGetLastError() == cudaSuccess &&
+             cudaMemcpy(out_density + (size_t)p0 * K, d_od, (size_t)np * K * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaMemcpy(out_quanta + (size_t)p0 * K, d_oq, (size_t)np * K * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaMemcpy(out_lut + (size_t)p0 * stride, d_lut, (size_t)np * stride * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (!ok) rc = fail(PD_ECUDA, "optls kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cleanup();
     return rc;
 }
 
