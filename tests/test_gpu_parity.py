@@ -68,6 +68,13 @@ BIG = [
     ("FastSCLLUTDecoder", dict(N=256, K=64, L=2, B=500)),
     ("FastSCLUTDecoder", dict(N=1024, K=700, B=1000)),            # wide R1 / SPC nodes in the non-list warp path
     ("FastSCLUTDecoder", dict(N=64, K=40, B=1000)),
+    # fp64 LLR family at large N (workspace levels beyond L2 reach)
+    ("SCDecoder", dict(N=1024, K=512, B=300)),
+    ("FastSCDecoder", dict(N=1024, K=700, B=300)),
+    ("SCLDecoder", dict(N=1024, K=512, L=8, B=60)),
+    ("FastSCLDecoder", dict(N=512, K=256, L=4, B=100)),
+    ("CASCLDecoder", dict(N=512, K=280, A=256, L=8, B=60)),
+    ("FastSCLDecoder", dict(N=2048, K=1500, L=2, B=30)),
     ("SCLUTDecoder", dict(N=32, K=16, B=1000)),
     ("SCLLUTDecoder", dict(N=32, K=16, L=8, B=1000)),
     ("SCLLUTDecoder", dict(N=2048, K=1024, L=8, B=60, construction="pw")),
