@@ -295,6 +295,22 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             if (isg) t1 = next_line();
             const uint32_t *src = (dd == 0) ? G + grp : level_ptr(dd, vslot(dd));
             const int sstride = (dd == 0) ? FPW : 32;
+            if (!FAST && L > 1 && !isg && node == 0) {   // (not in the Fast variant: it is instruction-fetch bound, the extra code costs 10 % there)
+                // leftmost chain of the tree: f outputs of f outputs of the channel symbols depend on no decision, so all L
+                // paths of a frame hold the same words.  Computed once per frame -- the lanes split the words -- into slot 0
+                // of the group, which every path then points to (the source is shared the same way, by induction).
+                uint32_t *dst0 = level_ptr(dd + 1, gbase);
+                const int nw0 = ct >> 3;
+                for (int w0 = 0; w0 < nw0; w0 += L) {   // (every lane takes part in the lookup shuffles, also when nw0 < L)
+                    const bool act = w0 + me < nw0;
+                    const int w = act ? w0 + me : 0;
+                    const uint32_t o = lookup8(src[w * sstride], src[(nw0 + w) * sstride], 0u, t0, t0, std::false_type{});
+                    if (act) dst0[w * 32] = o;
+                }
+                pv &= ~(7u << (3 * dd));            // level dd+1 -> slot 0
+                __syncwarp();
+                return;
+            }
             uint32_t *dst = level_ptr(dd + 1, lane);
             const uint32_t *xsrc = X + uslot(dd + 1);
             const uint32_t ub0 = (2u * node) * (uint32_t)ct;
