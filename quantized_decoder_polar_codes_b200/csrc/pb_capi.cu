@@ -113,6 +113,7 @@ struct pd_decoder {
     size_t ws_user_cap = 0;
     StreamSlot slot[2];
     int64_t chunk_frames = 0;
+    int grid_div = 1;         // pd_decode_device, split batches: 2 = each concurrent launch takes half of the CTA slots (experiment knob)
     // pd_decode, tiny calls (the reference drivers decode one frame per call): a mapped pinned staging area the kernel
     // reads and writes directly -- no copy engine round trips
     char *h_small = nullptr, *d_small = nullptr;
@@ -336,7 +337,7 @@ bool want_path(const pd_decoder *D, int dtype, const void *d_in) {
 int launch(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws) {
     if (B <= 0) return PD_OK;
     if (want_fast(D, dtype, d_in)) {
-        int rc = launch_fast_lut(D->dev, D->fast, d_in, dtype, B, d_out, s, reinterpret_cast<uint32_t *>(ws), D->d_err, D->dbg_pm, D->dbg_win, D->sm_count);
+        int rc = launch_fast_lut(D->dev, D->fast, d_in, dtype, B, d_out, s, reinterpret_cast<uint32_t *>(ws), D->d_err, D->dbg_pm, D->dbg_win, std::max(1, D->sm_count / D->grid_div));
         g_launches++;
         if (rc != 0) return fail(PD_ECUDA, "fast kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         return PD_OK;
@@ -567,14 +568,23 @@ int pd_decode_device(pd_decoder *D, const void *dev_in, int in_dtype, int64_t B,
     }
     CUDA_TRY(cudaEventRecord(D->fork_ev, s));
     for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamWaitEvent(D->side[i], D->fork_ev, 0));
+    // Both pieces in flight use a full grid and their own value workspace (2 x 52 MB at N=1024, L=8): together with the
+    // streaming input / output that exceeds the 126 MB L2, so part of the workspace is written back and re-read (ncu,
+    // --cache-control none: 5.2 KB of DRAM traffic per frame vs 1.5 KB algorithmic = 65 GB/s, 1 % of the HBM peak).
+    // POLAR_B200_HALF_GRID_PIECES=1 gives each piece half of the CTA slots instead: traffic 2.2 KB/frame, but 10 % fewer
+    // frames/s (the pieces no longer back-fill each other's tails) -- measured, not the default.
+    D->grid_div = getenv("POLAR_B200_HALF_GRID_PIECES") ? 2 : 1;
     for (int pc = 0; pc < pieces; ++pc) {
         const int64_t f0 = (int64_t)pc * per, nb = std::min<int64_t>(per, B - f0);
         if (nb <= 0) break;
         const int w = pc & 1;
         if ((rc = launch(D, (const char *)dev_in + (size_t)f0 * N * esz, in_dtype, nb, dev_out + (size_t)f0 * Ko, D->side[w],
-                         D->ws_user ? D->ws_user + (size_t)w * need1 : nullptr)))
+                         D->ws_user ? D->ws_user + (size_t)w * need1 : nullptr))) {
+            D->grid_div = 1;
             return rc;
+        }
     }
+    D->grid_div = 1;
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(cudaEventRecord(D->join_ev[i], D->side[i]));
         CUDA_TRY(cudaStreamWaitEvent(s, D->join_ev[i], 0));
