@@ -1,4 +1,5 @@
 #!/bin/bash
+# Round-end check on a B200 box: all GPU tests, smoke(), both bench arms and the per-shape survey (writes under gpurun_out/).
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 python bench.py > gpurun_out/bench_r1_g.json 2> gpurun_out/bench_r1_g.err; tail -2 gpurun_out/bench_r1_g.err; cat gpurun_out/bench_r1_g.json
