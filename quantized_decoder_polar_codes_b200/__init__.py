@@ -15,13 +15,20 @@ import sys as _sys
 
 _HERE = _os.path.dirname(_os.path.abspath(__file__))
 
+# `python -m quantized_decoder_polar_codes_b200.build` imports this package before the extension exists
+_BUILDING = (__name__ + ".build") in getattr(_sys, "orig_argv", [])
+
 try:
-    from . import _libPolarDecoder  # noqa: F401
+    if not _BUILDING:
+        from . import _libPolarDecoder  # noqa: F401
 except ImportError as _e:  # pragma: no cover
     raise ImportError(
         "quantized_decoder_polar_codes_b200: the native extension is not built "
         "(run `python -m quantized_decoder_polar_codes_b200.build`); there is no CPU fallback. "
         f"Original error: {_e}") from _e
+
+if _BUILDING:
+    _libPolarDecoder = None
 
 DECODER_CLASSES = (
     "SCDecoder", "FastSCDecoder", "SCLDecoder", "FastSCLDecoder", "CASCLDecoder",
@@ -29,12 +36,13 @@ DECODER_CLASSES = (
     "CAFastSCLLUTDecoder", "SCUniformQuantizedDecoder", "SCLUniformQuantizedDecoder",
     "SCLloydQuantizedDecoder", "SCLLloydQuantizedDecoder",
 )
-for _n in DECODER_CLASSES:
-    globals()[_n] = getattr(_libPolarDecoder, _n)
-del _n
-# blind-detection helpers of the reference's PolarEncoder/PolarBD package
-BDDMetricCalculator = _libPolarDecoder.BDDMetricCalculator
-BDCASCLDecoder = _libPolarDecoder.BDCASCLDecoder
+if not _BUILDING:
+    for _n in DECODER_CLASSES:
+        globals()[_n] = getattr(_libPolarDecoder, _n)
+    del _n
+    # blind-detection helpers of the reference's PolarEncoder/PolarBD package
+    BDDMetricCalculator = _libPolarDecoder.BDDMetricCalculator
+    BDCASCLDecoder = _libPolarDecoder.BDCASCLDecoder
 
 LIB_PATH = _os.path.join(_HERE, "libpolar_b200.so")
 

@@ -36,12 +36,44 @@ def _sources(exts):
     return out
 
 
+# translation units of libpolar_b200.so: (object name, source, extra flags, headers it depends on besides its source)
+_COMMON = ["pb_internal.h", "pb_generic.cuh"]
+_UNITS = [("capi", "pb_capi.cu", [], None)]          # None = every header
+_UNITS += [("k%d" % t, "pb_kernels.cu", ["-DPB_TU=%d" % t], _COMMON + ["pb_scl_lut.cuh"]) for t in (1, 2, 3, 4)]
+_UNITS += [("k%d" % t, "pb_kernels.cu", ["-DPB_TU=%d" % t], _COMMON + ["pb_path_warp.cuh"]) for t in (5, 6, 7, 8)]
+_UNITS += [("k9", "pb_kernels.cu", ["-DPB_TU=9"], _COMMON)]
+_UNITS += [("lutgen", "pb_lutgen.cu", [], ["pb_lutgen.cuh"])]
+OBJDIR = os.path.join(HERE, "build")
+
+
 def build_cuda(force=False, verbose=False):
-    srcs = _sources((".cu", ".cuh", ".h"))
-    if force or _newer(LIB, srcs):
-        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "pb_capi.cu"), "-o", LIB]
-        subprocess.check_call(cmd)
+    """Compile the translation units in parallel (one nvcc per object), then link."""
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(OBJDIR, exist_ok=True)
+    allhdr = _sources((".cuh", ".h"))
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    jobs, objs = [], []
+    for name, src, extra, deps in _UNITS:
+        obj = os.path.join(OBJDIR, name + ".o")
+        objs.append(obj)
+        dep = [os.path.join(CSRC, src)] + (allhdr if deps is None else [os.path.join(CSRC, d) for d in deps])
+        if force or _newer(obj, dep):
+            jobs.append([nvcc] + flags + extra + ["-c", os.path.join(CSRC, src), "-o", obj])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            def run(c):
+                import time
+                t0 = time.time()
+                rc = subprocess.call(c)
+                if verbose:
+                    print("[build] %s: %.0f s" % (os.path.basename(c[-1]), time.time() - t0), flush=True)
+                return rc
+            for rc, cmd in zip(ex.map(run, jobs), jobs):
+                if rc != 0:
+                    raise subprocess.CalledProcessError(rc, cmd)
+    if jobs or not os.path.exists(LIB):
+        subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
     return LIB
 
 

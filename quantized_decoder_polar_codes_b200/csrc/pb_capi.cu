@@ -23,9 +23,37 @@
 #include "pb_path_warp.cuh"
 #include "pb_sim.cuh"
 #include "pb_enc.cuh"
-#include "pb_lutgen.cuh"
 
 using namespace pb;
+
+// dispatchers over the kernel objects (pb_kernels.cu)
+namespace pb {
+const void *scl_fn_l3_plain(bool ca);
+const void *scl_fn_l3_fast(bool ca);
+const void *scl_fn_l01(int logL, bool ca, bool fast);
+const void *scl_fn_l2(bool ca, bool fast);
+const void *path_fn_lut(int logL);
+const void *path_fn_float(int logL);
+const void *path_fn_uniform(int logL);
+const void *path_fn_lloyd(int logL);
+// pb_lutgen.cu (its own object: the compile-time-unrolled pairwise sums take minutes to build)
+constexpr int kOptlsMaxM = 1024;
+cudaError_t launch_optls(int n_problems, size_t smem, const double *density, const double *quanta, const int32_t *M, long long stride, int K,
+                         double *out_density, double *out_quanta, int32_t *out_lut, double *T, int32_t *lm, long long t_stride, long long lm_stride);
+const void *fast_kernel_fn(int logL, bool ca, bool fast) {
+    if (logL >= 3) return fast ? scl_fn_l3_fast(ca) : scl_fn_l3_plain(ca);
+    if (logL == 2) return scl_fn_l2(ca, fast);
+    return scl_fn_l01(logL, ca, fast);
+}
+const void *path_kernel_fn(int dom, int logL) {
+    switch (dom) {
+    case DOM_LUT: return path_fn_lut(logL);
+    case DOM_FLOAT: return path_fn_float(logL);
+    case DOM_UNIFORM: return path_fn_uniform(logL);
+    default: return path_fn_lloyd(logL);
+    }
+}
+}  // namespace pb
 
 namespace {
 
@@ -262,31 +290,9 @@ int build_lut(pd_decoder *D, const pd_config *c) {
     return PD_OK;
 }
 
-template <int DOM, bool LIST>
-int launch_generic_t(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws, int grid) {
-    size_t smem = D->use_smem ? D->ws_bytes : 0;
-    if (D->threads == 32)
-        generic_decode_kernel<DOM, LIST, true><<<grid, 32, smem, s>>>(D->dev, d_in, dtype, d_out, B, ws, D->ws_bytes, D->use_smem, D->d_err, D->dbg_pm, D->dbg_win);
-    else
-        generic_decode_kernel<DOM, LIST, false><<<grid, D->threads, smem, s>>>(D->dev, d_in, dtype, d_out, B, ws, D->ws_bytes, D->use_smem, D->d_err, D->dbg_pm, D->dbg_win);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    return PD_OK;
-}
-
-template <int DOM, bool LIST>
-const void *generic_fn(bool warp) {
-    return warp ? (const void *)generic_decode_kernel<DOM, LIST, true> : (const void *)generic_decode_kernel<DOM, LIST, false>;
-}
+// kernel instantiations live in pb_kernels.cu (one object per family, compiled in parallel)
 const void *generic_fn_for(const pd_decoder *D) {
-    bool w = D->threads == 32;
-    bool l = D->dev.list != 0;
-    switch (D->dev.domain) {
-    case DOM_LUT: return l ? generic_fn<DOM_LUT, true>(w) : generic_fn<DOM_LUT, false>(w);
-    case DOM_FLOAT: return l ? generic_fn<DOM_FLOAT, true>(w) : generic_fn<DOM_FLOAT, false>(w);
-    case DOM_UNIFORM: return l ? generic_fn<DOM_UNIFORM, true>(w) : generic_fn<DOM_UNIFORM, false>(w);
-    default: return l ? generic_fn<DOM_LLOYD, true>(w) : generic_fn<DOM_LLOYD, false>(w);
-    }
+    return pb::generic_kernel_fn(D->dev.domain, D->dev.list != 0, D->threads == 32);
 }
 
 int generic_grid(const pd_decoder *D, int64_t B) {
@@ -296,13 +302,14 @@ int generic_grid(const pd_decoder *D, int64_t B) {
 
 int launch_generic(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out, cudaStream_t s, char *ws) {
     int grid = generic_grid(D, B);
-    bool l = D->dev.list != 0;
-    switch (D->dev.domain) {
-    case DOM_LUT: return l ? launch_generic_t<DOM_LUT, true>(D, d_in, dtype, B, d_out, s, ws, grid) : launch_generic_t<DOM_LUT, false>(D, d_in, dtype, B, d_out, s, ws, grid);
-    case DOM_FLOAT: return l ? launch_generic_t<DOM_FLOAT, true>(D, d_in, dtype, B, d_out, s, ws, grid) : launch_generic_t<DOM_FLOAT, false>(D, d_in, dtype, B, d_out, s, ws, grid);
-    case DOM_UNIFORM: return l ? launch_generic_t<DOM_UNIFORM, true>(D, d_in, dtype, B, d_out, s, ws, grid) : launch_generic_t<DOM_UNIFORM, false>(D, d_in, dtype, B, d_out, s, ws, grid);
-    default: return l ? launch_generic_t<DOM_LLOYD, true>(D, d_in, dtype, B, d_out, s, ws, grid) : launch_generic_t<DOM_LLOYD, false>(D, d_in, dtype, B, d_out, s, ws, grid);
-    }
+    size_t smem = D->use_smem ? D->ws_bytes : 0;
+    long long Bll = B;
+    void *args[] = {(void *)&D->dev, (void *)&d_in, (void *)&dtype, (void *)&d_out, (void *)&Bll, (void *)&ws, (void *)&D->ws_bytes,
+                    (void *)&D->use_smem, (void *)&D->d_err, (void *)&D->dbg_pm, (void *)&D->dbg_win};
+    CUDA_TRY(cudaLaunchKernel(generic_fn_for(D), dim3(grid), dim3(D->threads), args, smem, s));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PD_OK;
 }
 
 int plan_generic(pd_decoder *D) {
@@ -953,9 +960,9 @@ int pd_optls_quantize(const double *density, const double *quanta, const int32_t
                   cudaMemcpy(d_q, quanta + (size_t)p0 * stride, (size_t)np * stride * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
                   cudaMemcpy(d_M, M + p0, (size_t)np * 4, cudaMemcpyHostToDevice) == cudaSuccess;
         if (!ok) { rc = fail(PD_ECUDA, "H2D copy failed"); break; }
-        optls_kernel<<<np, 256, smem>>>(d_d, d_q, d_M, stride, K, d_od, d_oq, d_lut, d_T, d_lm, t_stride, lm_stride);
+        const cudaError_t le = launch_optls(np, smem, d_d, d_q, d_M, stride, K, d_od, d_oq, d_lut, d_T, d_lm, t_stride, lm_stride);
         g_launches++;
-        ok = cudaGetLastError() == cudaSuccess &&
+        ok = le == cudaSuccess &&
              cudaMemcpy(out_density + (size_t)p0 * K, d_od, (size_t)np * K * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
              cudaMemcpy(out_quanta + (size_t)p0 * K, d_oq, (size_t)np * K * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
              cudaMemcpy(out_lut + (size_t)p0 * stride, d_lut, (size_t)np * stride * 4, cudaMemcpyDeviceToHost) == cudaSuccess;

@@ -622,4 +622,6 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
 #undef OFFUR
 }
 
+const void *generic_kernel_fn(int dom, bool list, bool warp);   // instantiations: pb_kernels.cu
+
 }  // namespace pb

@@ -509,6 +509,8 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
 }
 
 // ------------------------------------------------------------------------------------------------
+const void *path_kernel_fn(int dom, int logL);   // instantiations: pb_kernels.cu
+#ifdef PB_TU_PATH
 template <int DOM>
 inline const void *path_kernel_fn_d(int logL) {
     switch (logL) {
@@ -520,14 +522,7 @@ inline const void *path_kernel_fn_d(int logL) {
     default: return (const void *)path_warp_kernel<DOM, 5>;
     }
 }
-inline const void *path_kernel_fn(int dom, int logL) {
-    switch (dom) {
-    case DOM_LUT: return path_kernel_fn_d<DOM_LUT>(logL);
-    case DOM_FLOAT: return path_kernel_fn_d<DOM_FLOAT>(logL);
-    case DOM_UNIFORM: return path_kernel_fn_d<DOM_UNIFORM>(logL);
-    default: return path_kernel_fn_d<DOM_LLOYD>(logL);
-    }
-}
+#endif
 
 inline void plan_path_warp(const Dev &d, PathPlan *pl) {
     pl->ok = false;

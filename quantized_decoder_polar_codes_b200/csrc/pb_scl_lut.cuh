@@ -99,7 +99,7 @@ struct R1Acc {
 struct R1Less {
     __device__ __forceinline__ bool operator()(unsigned short x, unsigned short y) const { return (x >> 5) < (y >> 5); }
 };
-__device__ __noinline__ void sort_r1_packed(unsigned short *col, int n) { std_sort_acc<16>(R1Acc{col}, n, R1Less{}); }
+static __device__ __noinline__ void sort_r1_packed(unsigned short *col, int n) { std_sort_acc<16>(R1Acc{col}, n, R1Less{}); }
 
 struct RingState {
     unsigned fetch_off;   // byte offset (within the stream) of the next chunk to prefetch
@@ -121,7 +121,7 @@ __device__ __forceinline__ uint4 ring_next_chunk(RingState &rs, unsigned ring_la
 }
 // out-of-line refill for the Fast-SSC variant (~40 consumption sites): everything travels in registers, the caller
 // advances the ring state itself
-__device__ __noinline__ uint4 ring_fetch_outlined(unsigned fetch_off, unsigned chunk_no, unsigned ring_lane, const char *stream_lane) {
+static __device__ __noinline__ uint4 ring_fetch_outlined(unsigned fetch_off, unsigned chunk_no, unsigned ring_lane, const char *stream_lane) {
     const unsigned slot = chunk_no & (kRingChunks - 1);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(ring_lane + ((slot + kRingChunks - 1) & (kRingChunks - 1)) * 512u), "l"(stream_lane + fetch_off));
     cp_async_wait<kRingChunks - 1>();
@@ -846,20 +846,17 @@ inline bool fast_upload(FastPlan *pl, const std::vector<T> &h, const T **out) {
     return true;
 }
 
+// Kernel instantiations live in their own translation units (pb_kernels.cu, compiled in parallel); the host side only
+// sees the dispatcher.
+const void *fast_kernel_fn(int logL, bool ca, bool fast);
+#ifdef PB_TU_SCL
 template <int LOGL>
 inline const void *fast_kernel_fn_l(bool ca, bool fast) {
     if (LOGL == 0) return fast ? (const void *)scl_lut_warp_kernel<0, false, true> : (const void *)scl_lut_warp_kernel<0, false, false>;
     if (ca) return fast ? (const void *)scl_lut_warp_kernel<LOGL, true, true> : (const void *)scl_lut_warp_kernel<LOGL, true, false>;
     return fast ? (const void *)scl_lut_warp_kernel<LOGL, false, true> : (const void *)scl_lut_warp_kernel<LOGL, false, false>;
 }
-inline const void *fast_kernel_fn(int logL, bool ca, bool fast) {
-    switch (logL) {
-    case 0: return fast_kernel_fn_l<0>(false, fast);
-    case 1: return fast_kernel_fn_l<1>(ca, fast);
-    case 2: return fast_kernel_fn_l<2>(ca, fast);
-    default: return fast_kernel_fn_l<3>(ca, fast);
-    }
-}
+#endif
 
 // Decide whether the specialised kernel applies; if so compile the reference's tree walk into the op list and
 // lay the tables out as one stream in consumption order.
