@@ -21,8 +21,10 @@
 #include "pb_generic.cuh"
 #include "pb_scl_lut.cuh"
 #include "pb_path_warp.cuh"
+#ifndef PB_HOST_EMU   // (tools/emu emulates the decode kernels only)
 #include "pb_sim.cuh"
 #include "pb_enc.cuh"
+#endif
 
 using namespace pb;
 
@@ -727,6 +729,7 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
     return pd_check(D, D->slot[1].stream);
 }
 
+#ifndef PB_HOST_EMU
 // ---- simulation-mode error counters -------------------------------------------------------------
 __global__ void count_errors_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, long long B, int len,
                                     unsigned long long *counters) {
@@ -971,6 +974,8 @@ int pd_optls_quantize(const double *density, const double *quanta, const int32_t
     cleanup();
     return rc;
 }
+
+#endif   // PB_HOST_EMU
 
 void *pd_host_alloc(size_t bytes) {
     void *p = nullptr;

@@ -270,7 +270,7 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
                       long long B, char *ws, size_t ws_stride, int use_smem, int *err_flag,
                       double *dbg_pm, int *dbg_win) {
     using T = typename Val<DOM>::T;
-    extern __shared__ __align__(16) char dyn_smem[];
+    PB_DYN_SMEM(char, dyn_smem);
     __shared__ Ctl c;
 
     const int tid = threadIdx.x, nth = blockDim.x;

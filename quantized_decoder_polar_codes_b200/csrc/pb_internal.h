@@ -2,6 +2,16 @@
 #pragma once
 #include <cstdint>
 
+// Dynamic shared memory / kernel handles.  PB_HOST_EMU (tools/emu: CPU fibers, development only) swaps them for
+// host equivalents; the product build never defines it.
+#ifdef PB_HOST_EMU
+#define PB_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(pb_emu::dyn_smem())
+#define PB_KFN(...) pb_emu::reg(__VA_ARGS__)
+#else
+#define PB_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define PB_KFN(...) ((const void *)(__VA_ARGS__))
+#endif
+
 namespace pb {
 
 constexpr int kMaxL = 32;

@@ -9,13 +9,14 @@
 #include "pb_scl_lut.cuh"
 namespace pb {
 #if PB_TU == 1
-const void *scl_fn_l3_plain(bool ca) { return fast_kernel_fn_l<3>(ca, false); }
+const void *scl_fn_l3_plain(bool ca) { return fast_kernel_fn_l<3, false>(ca); }
 #elif PB_TU == 2
-const void *scl_fn_l3_fast(bool ca) { return fast_kernel_fn_l<3>(ca, true); }
+const void *scl_fn_l3_fast(bool ca) { return fast_kernel_fn_l<3, true>(ca); }
 #elif PB_TU == 3
-const void *scl_fn_l01(int logL, bool ca, bool fast) { return logL == 0 ? fast_kernel_fn_l<0>(false, fast) : fast_kernel_fn_l<1>(ca, fast); }
+const void *scl_fn_l01(int logL, bool ca, bool fast) { if (logL == 0) return fast ? fast_kernel_fn_l<0, true>(false) : fast_kernel_fn_l<0, false>(false);
+    return fast ? fast_kernel_fn_l<1, true>(ca) : fast_kernel_fn_l<1, false>(ca); }
 #else
-const void *scl_fn_l2(bool ca, bool fast) { return fast_kernel_fn_l<2>(ca, fast); }
+const void *scl_fn_l2(bool ca, bool fast) { return fast ? fast_kernel_fn_l<2, true>(ca) : fast_kernel_fn_l<2, false>(ca); }
 #endif
 }  // namespace pb
 #elif PB_TU >= 5 && PB_TU <= 8
@@ -38,7 +39,7 @@ const void *path_fn_lloyd(int logL) { return path_kernel_fn_d<DOM_LLOYD>(logL); 
 namespace pb {
 template <int DOM, bool LIST>
 static const void *generic_fn(bool warp) {
-    return warp ? (const void *)generic_decode_kernel<DOM, LIST, true> : (const void *)generic_decode_kernel<DOM, LIST, false>;
+    return warp ? PB_KFN(generic_decode_kernel<DOM, LIST, true>) : PB_KFN(generic_decode_kernel<DOM, LIST, false>);
 }
 const void *generic_kernel_fn(int dom, bool l, bool w) {
     switch (dom) {

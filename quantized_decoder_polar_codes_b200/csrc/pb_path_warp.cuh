@@ -61,7 +61,7 @@ path_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ PathPara
     constexpr int L = 1 << LOGL;
     constexpr int FPW = 32 / L;
     constexpr unsigned kAll = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smraw[];
+    PB_DYN_SMEM(unsigned char, smraw);
     const int lane = threadIdx.x;
     const int grp = lane >> LOGL, me = lane & (L - 1), gbase = lane & ~(L - 1);
     const int N = d.N, n = d.n;
@@ -514,12 +514,12 @@ const void *path_kernel_fn(int dom, int logL);   // instantiations: pb_kernels.c
 template <int DOM>
 inline const void *path_kernel_fn_d(int logL) {
     switch (logL) {
-    case 0: return (const void *)path_warp_kernel<DOM, 0>;
-    case 1: return (const void *)path_warp_kernel<DOM, 1>;
-    case 2: return (const void *)path_warp_kernel<DOM, 2>;
-    case 3: return (const void *)path_warp_kernel<DOM, 3>;
-    case 4: return (const void *)path_warp_kernel<DOM, 4>;
-    default: return (const void *)path_warp_kernel<DOM, 5>;
+    case 0: return PB_KFN(path_warp_kernel<DOM, 0>);
+    case 1: return PB_KFN(path_warp_kernel<DOM, 1>);
+    case 2: return PB_KFN(path_warp_kernel<DOM, 2>);
+    case 3: return PB_KFN(path_warp_kernel<DOM, 3>);
+    case 4: return PB_KFN(path_warp_kernel<DOM, 4>);
+    default: return PB_KFN(path_warp_kernel<DOM, 5>);
     }
 }
 #endif

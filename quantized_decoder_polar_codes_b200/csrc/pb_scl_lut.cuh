@@ -78,15 +78,28 @@ struct FastPlan {
     std::vector<void *> allocs;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint4 *gsrc) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
-    asm volatile("cp.async.commit_group;\n" ::);
+// shared-memory address of the asynchronous-copy primitives: a 32-bit shared-window address on the device, a plain
+// pointer value in the host emulation (tools/emu)
+#ifdef PB_HOST_EMU
+using smaddr_t = size_t;
+__device__ __forceinline__ void ldgsts16(smaddr_t dst, const void *gsrc) { memcpy(reinterpret_cast<void *>(dst), gsrc, 16); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() {}
+__device__ __forceinline__ uint4 lds128(smaddr_t a) { uint4 v; memcpy(&v, reinterpret_cast<const void *>(a), 16); return v; }
+#else
+using smaddr_t = unsigned;
+__device__ __forceinline__ void ldgsts16(smaddr_t dst, const void *gsrc) {   // one committed cp.async group of 16 bytes
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(dst), "l"(gsrc));
 }
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory");
 }
+__device__ __forceinline__ uint4 lds128(smaddr_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+#endif
 
 // R1 nodes of the list Fast decoders: elements packed as rank<<5 | index, one column of a [element][32 lanes] array of
 // 16-bit words; std::sort order under "rank < rank" (equal ranks = equal |llr|: libstdc++'s introsort order)
@@ -105,36 +118,32 @@ struct RingState {
     unsigned fetch_off;   // byte offset (within the stream) of the next chunk to prefetch
     unsigned chunk_no;    // chunks consumed so far
 };
-__device__ __forceinline__ void ring_issue(RingState &rs, unsigned slot, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(ring_lane + slot * 512u), "l"(stream_lane + rs.fetch_off));
+__device__ __forceinline__ void ring_issue(RingState &rs, unsigned slot, smaddr_t ring_lane, const char *stream_lane, unsigned stream_bytes) {
+    ldgsts16(ring_lane + slot * 512u, stream_lane + rs.fetch_off);
     rs.fetch_off += 512u;
     if (rs.fetch_off == stream_bytes) rs.fetch_off = 0;
 }
-__device__ __forceinline__ uint4 ring_next_chunk(RingState &rs, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
+__device__ __forceinline__ uint4 ring_next_chunk(RingState &rs, smaddr_t ring_lane, const char *stream_lane, unsigned stream_bytes) {
     const unsigned slot = rs.chunk_no & (kRingChunks - 1);
     ring_issue(rs, (slot + kRingChunks - 1) & (kRingChunks - 1), ring_lane, stream_lane, stream_bytes);   // refill the slot consumed before
     cp_async_wait<kRingChunks - 1>();                                                                     // ... and make sure this chunk has landed
     ++rs.chunk_no;
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_lane + slot * 512u));
-    return v;
+    return lds128(ring_lane + slot * 512u);
 }
 // out-of-line refill for the Fast-SSC variant (~40 consumption sites): everything travels in registers, the caller
 // advances the ring state itself
-static __device__ __noinline__ uint4 ring_fetch_outlined(unsigned fetch_off, unsigned chunk_no, unsigned ring_lane, const char *stream_lane) {
+static __device__ __noinline__ uint4 ring_fetch_outlined(unsigned fetch_off, unsigned chunk_no, smaddr_t ring_lane, const char *stream_lane) {
     const unsigned slot = chunk_no & (kRingChunks - 1);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(ring_lane + ((slot + kRingChunks - 1) & (kRingChunks - 1)) * 512u), "l"(stream_lane + fetch_off));
+    ldgsts16(ring_lane + ((slot + kRingChunks - 1) & (kRingChunks - 1)) * 512u, stream_lane + fetch_off);
     cp_async_wait<kRingChunks - 1>();
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_lane + slot * 512u));
-    return v;
+    return lds128(ring_lane + slot * 512u);
 }
 struct LineState {
     RingState rs;
     uint4 cur;   // the chunk lines are currently taken from
     int q;       // next line inside `cur` (4 = exhausted)
 };
-__device__ __forceinline__ uint32_t next_line_inl(LineState &ls, unsigned ring_lane, const char *stream_lane, unsigned stream_bytes) {
+__device__ __forceinline__ uint32_t next_line_inl(LineState &ls, smaddr_t ring_lane, const char *stream_lane, unsigned stream_bytes) {
     if (ls.q == 4) { ls.cur = ring_next_chunk(ls.rs, ring_lane, stream_lane, stream_bytes); ls.q = 0; }
     const uint32_t v = ls.q == 0 ? ls.cur.x : ls.q == 1 ? ls.cur.y : ls.q == 2 ? ls.cur.z : ls.cur.w;
     ++ls.q;
@@ -153,7 +162,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                     uint8_t *__restrict__ out, long long B, uint32_t *__restrict__ ws, int *err_flag, double *dbg_pm, int *dbg_win) {
     constexpr int L = 1 << LOGL;
     constexpr int FPW = 32 / L;
-    extern __shared__ __align__(16) uint32_t sm[];
+    PB_DYN_SMEM(uint32_t, sm);
     const int lane = threadIdx.x;
     const int grp = lane >> LOGL, me = lane & (L - 1), gbase = lane & ~(L - 1);
     const int N = d.N, n = d.n;
@@ -164,7 +173,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     uint32_t *SCR = sm + fp.scr_off;                   // epilogue scratch [word][frame in warp] (L > 1)
     uint32_t *RING = X + fp.xwords * 32 + fp.scrwords; // [kRingChunks][lane][4]
     uint32_t *G = ws + (size_t)blockIdx.x * fp.gwords * 32;   // value levels 1..gl, [word][lane], L2-resident
-    double *KS = reinterpret_cast<double *>(RING + kRingChunks * 128);   // [32][2]
+    double *KS = reinterpret_cast<double *>(RING + kRingChunks * 128);   // key pairs (keep, flip), [path][frame in warp][2]: the FPW groups read adjacent 16-byte cells
     uint32_t *SEL = reinterpret_cast<uint32_t *>(KS + 64);               // [32]
     double *R1S = reinterpret_cast<double *>(SEL + 32);                  // [7][32] smallest |llr| of an R1 node (Fast kinds)
     uint32_t *R1Q = reinterpret_cast<uint32_t *>(R1S + 7 * 32);          // [7][32] their positions
@@ -178,7 +187,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     ls.rs.fetch_off = 0u; ls.rs.chunk_no = 0u; ls.cur = make_uint4(0, 0, 0, 0); ls.q = 4;
     const unsigned stream_bytes = (unsigned)fp.n_chunks * 512u;
     const char *stream_lane = reinterpret_cast<const char *>(fp.stream) + lane * 16;
-    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(RING + lane * 4);   // this lane's 16 bytes of slot 0
+    const smaddr_t ring_lane = (smaddr_t)__cvta_generic_to_shared(RING + lane * 4);   // this lane's 16 bytes of slot 0
     for (int i = 0; i < kRingChunks - 1; ++i) ring_issue(ls.rs, i, ring_lane, stream_lane, stream_bytes);
     // the Fast-SSC variant has ~40 consumption sites: there the stream accessors are real (out-of-line) functions so
     // that the hot code stays inside the instruction cache; the plain variant inlines them
@@ -372,14 +381,18 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         // parent path and the flip flag; PM, the pointer words and the subtree registers follow the parent.
         auto fork = [&](double K0, double K1, int &p, uint32_t &fl) {
             __syncwarp();
-            *reinterpret_cast<double2 *>(&KS[lane * 2]) = make_double2(K0, K1);
+            *reinterpret_cast<double2 *>(&KS[(me * FPW + grp) * 2]) = make_double2(K0, K1);
             __syncwarp();
             int r0 = 0, r1 = 0;
 #pragma unroll
             for (int j = 0; j < L; ++j) {
-                const double2 kf = *reinterpret_cast<const double2 *>(&KS[(gbase + j) * 2]);
+                const double2 kf = *reinterpret_cast<const double2 *>(&KS[(j * FPW + grp) * 2]);
                 // r0 += (keep_j,j) < (K0,me)  +  flip_j < K0 ;  r1 += keep_j <= K1  +  (flip_j,j) < (K1,me)
                 // (predicated adds: the compiler's bool->int lowering of the same expression costs 40 % more issue slots)
+#ifdef PB_HOST_EMU
+                r0 += (int)((kf.x < K0) || (kf.x <= K0 && j < me)) + (int)(kf.y < K0);
+                r1 += (int)(kf.x <= K1) + (int)((kf.y < K1) || (kf.y <= K1 && j < me));
+#else
                 asm("{\n"
                     " .reg .pred lt0, le0, f0, le1, lt1, lf1, jb, t0, t1;\n"
                     " setp.lt.s32 jb, %6, %7;\n"
@@ -400,6 +413,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                     "}\n"
                     : "+r"(r0), "+r"(r1)
                     : "d"(kf.x), "d"(kf.y), "d"(K0), "d"(K1), "r"(j), "r"(me));
+#endif
             }
             if (r0 < L) SEL[gbase + r0] = (uint32_t)me;
             if (r1 < L) SEL[gbase + r1] = (uint32_t)me | 16u;
@@ -407,7 +421,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             const uint32_t sv = SEL[lane];
             p = gbase | (int)(sv & 15u);
             fl = sv >> 4;
-            PM = KS[p * 2 + fl];
+            PM = KS[(((int)(sv & 15u)) * FPW + grp) * 2 + fl];
             w3 = __shfl_sync(kFull, w3, p);
             w21 = __shfl_sync(kFull, w21, p);
             xb = __shfl_sync(kFull, xb, p);
@@ -514,7 +528,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                     const double l = llr_of(elem_line(j), nib(sw, j & 7));
                     const double al = fabs(l);
                     if (spt == 0) {
-                        PM += (double)(float)(l < 0) * al;
+                        if (l < 0) PM += al;
                     } else {
                         a0 += (double)(l < 0) * al;
                         a1 += (double)(l >= 0) * al;
@@ -722,7 +736,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                         if (L == 1) {
                             bit = (!frozen && DM <= 0) ? 1u : 0u;
                         } else if (frozen) {
-                            PM += fabs(DM) * (double)(DM < 0);
+                            if (DM < 0) PM += fabs(DM);
                         } else {
                             const uint32_t dec = (DM < 0) ? 1u : 0u;
                             int p;
@@ -850,11 +864,10 @@ inline bool fast_upload(FastPlan *pl, const std::vector<T> &h, const T **out) {
 // sees the dispatcher.
 const void *fast_kernel_fn(int logL, bool ca, bool fast);
 #ifdef PB_TU_SCL
-template <int LOGL>
-inline const void *fast_kernel_fn_l(bool ca, bool fast) {
-    if (LOGL == 0) return fast ? (const void *)scl_lut_warp_kernel<0, false, true> : (const void *)scl_lut_warp_kernel<0, false, false>;
-    if (ca) return fast ? (const void *)scl_lut_warp_kernel<LOGL, true, true> : (const void *)scl_lut_warp_kernel<LOGL, true, false>;
-    return fast ? (const void *)scl_lut_warp_kernel<LOGL, false, true> : (const void *)scl_lut_warp_kernel<LOGL, false, false>;
+template <int LOGL, bool FAST>
+inline const void *fast_kernel_fn_l(bool ca) {
+    if (LOGL == 0 || !ca) return PB_KFN(scl_lut_warp_kernel<LOGL, false, FAST>);
+    return PB_KFN(scl_lut_warp_kernel<LOGL, (LOGL > 0), FAST>);
 }
 #endif
 
