@@ -214,11 +214,16 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     D.init("nccl", dev)
-    F = args.batch
-    kw, sym0, msg0 = make_workload(min(F, 8192), seed=rank)
-    sym, msg = tile_frames(sym0, msg0, F)
+    kw, sym0, msg0 = make_workload(8192, seed=rank)
     dec = q.SCLLUTDecoder(device=local_rank, **kw)
     lib = capi.lib()
+    # frames per step: --batch, or by default the multiple of the kernel's wave (SMs x resident warps x frames per warp)
+    # nearest to 131072 -- a persistent kernel then has no tail
+    F = args.batch
+    wave = capi.wave_frames(dec, capi.PD_U8)
+    if F <= 0:
+        F = max(1, round(131072 / wave)) * wave if wave > 0 else 131072
+    sym, msg = tile_frames(sym0, msg0, F)
     stream = torch.cuda.current_stream().cuda_stream
 
     d_in = torch.from_numpy(sym).to(dev)
@@ -226,7 +231,7 @@ def run_ours(args, rank, local_rank, world):
     d_out = torch.empty((F, K), dtype=torch.uint8, device=dev)
     counters = torch.zeros(2, dtype=torch.int64, device=dev)   # run totals (identical on every rank)
     step_cnt = torch.zeros(2, dtype=torch.int64, device=dev)   # this step's local counts -> all-reduced -> added to the totals
-    assert d_in.numel() >= 126 * 2 ** 20 or args.batch < 131072, "inputs must exceed L2"
+    assert d_in.numel() >= 120 * 2 ** 20 or 0 < args.batch < 131072, "inputs + outputs of a step must exceed L2"
 
     def count_and_reduce():
         step_cnt.zero_()
@@ -310,7 +315,7 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "info_gbit_s": value * K / 1e9, "kernel": dec.kernel,
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "wave_frames": wave, "info_gbit_s": value * K / 1e9, "kernel": dec.kernel,
                        "l2": "inputs+outputs per step exceed L2 (no flush needed)" if F * BYTES_PER_FRAME > 126 * 2 ** 20 else "batch below L2 size",
                        "bit_errors": cnt[0], "block_errors": cnt[1], "frames_counted": total_frames,
                        "e2e_equals_device_output": same},
@@ -361,7 +366,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=131072, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (default: the whole number of kernel waves nearest to 131072)")
     ap.add_argument("--ref-frames", type=int, default=400, help="CPU reference: frames per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -106,6 +106,10 @@ void pd_destroy(pd_decoder *dec);
  * CASCLLUTDecoder.cpp:290). */
 int pd_out_len(const pd_decoder *dec);
 int pd_code_len(const pd_decoder *dec);
+/* Frames that one full wave of the (persistent) decode kernel holds in flight on the decoder's GPU: SMs x resident warps x
+ * frames per warp; 0 for the CTA-per-frame generic kernel.  A batch that is a multiple of it keeps every warp busy until the
+ * last frame (no tail); pd_decode_device cuts other large batches into overlapping launches instead. */
+int64_t pd_wave_frames(const pd_decoder *dec, int in_dtype);
 
 /* Replaces `T::decode(array)` (e.g. SCLLUT::decode, PD/src/SCLLUTDecoder.cpp:47) for a batch of B frames.
  * host_in: [B][N] of `in_dtype`, C-contiguous; host_out: [B][pd_out_len] uint8.  Blocking: pipelines
@@ -196,6 +200,21 @@ int pd_sim_encode_device(pd_sim *sim, int mode, const uint8_t *dev_in, int64_t B
  * Host buffers; runs on `device`. */
 int pd_optls_quantize(const double *density, const double *quanta, const int32_t *M, int64_t stride, int32_t P, int32_t K,
                       double *out_density, double *out_quanta, int32_t *out_lut, int32_t device);
+
+/* Probability-domain table design (the other half of SURVEY 8f row f3): the device passes of the maximum-mutual-information
+ * quantizer MMIQuantizer.find_opt_quantizer that QDensityEvolution_MMI.py:84,107 runs on every tree node (C++ on OpenCV in
+ * Quantizers/quantizers/_cpp/MMIQuantizer/MMIQuantizer.cpp:73-165; numpy restatement QuantizeDensityEvolution/MMIQuantizer.py:
+ * 36-84,158-225, which this follows bit for bit).  P problems of M symbols each, sorted by likelihood ratio, conditional
+ * probabilities p1[p][i] = P(y_i|x=+1), p2[p][i] = P(y_i|x=-1); K output symbols; W = M-K+1.  Tables are banded: entry
+ * [p][a'][w] describes merging the sorted symbols a' .. a'+w into one.
+ *   pd_mmi_slice_sums: sum1/sum2[p][a'][w] = np.sum(p1/p2[a' : a'+w+1]) in numpy's pairwise order (MMIQuantizer.py:42-43).
+ *   pd_mmi_design:     cost[p][a'][w] = c1*np.sum(p1[..]*l1[p][a'][w]) + c2*np.sum(p2[..]*l2[p][a'][w]) (:55-67; l = log2 of the
+ *                      cluster likelihoods, taken by the caller with numpy so that they are numpy's), then the dynamic
+ *                      programme and back-trace (:175-215); Az[p][0..K] = cluster boundaries.
+ * Host buffers; runs on `device`. */
+int pd_mmi_slice_sums(const double *p1, const double *p2, int32_t P, int32_t M, int32_t K, double *sum1, double *sum2, int32_t device);
+int pd_mmi_design(const double *p1, const double *p2, const double *l1, const double *l2, double c1, double c2,
+                  int32_t P, int32_t M, int32_t K, int32_t *Az, int32_t device);
 
 /* Kernels launched by this library on the calling process so far (bench.py reports it as gpu_launches). */
 int64_t pd_launch_count(void);

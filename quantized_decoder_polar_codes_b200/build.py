@@ -72,7 +72,7 @@ def build_cuda(force=False, verbose=False):
             for rc, cmd in zip(ex.map(run, jobs), jobs):
                 if rc != 0:
                     raise subprocess.CalledProcessError(rc, cmd)
-    if jobs or not os.path.exists(LIB):
+    if jobs or _newer(LIB, objs):
         subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
     return LIB
 

@@ -26,6 +26,8 @@ def lib():
         L.pd_launch_count.restype = C.c_int64
         L.pd_out_len.argtypes = [C.c_void_p]
         L.pd_code_len.argtypes = [C.c_void_p]
+        L.pd_wave_frames.restype = C.c_int64
+        L.pd_wave_frames.argtypes = [C.c_void_p, C.c_int]
         L.pd_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
         L.pd_decode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         L.pd_check.argtypes = [C.c_void_p, C.c_void_p]
@@ -43,6 +45,8 @@ def lib():
         L.pd_sim_encode_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.pd_decode_bd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pd_decode_bd_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pd_mmi_slice_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        L.pd_mmi_design.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
         L.pd_optls_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         _lib = L
     return _lib
@@ -65,6 +69,11 @@ def decode_device(decoder, dev_in_ptr, dtype, B, dev_out_ptr, stream=0):
 
 def decode_host(decoder, host_in_ptr, dtype, B, host_out_ptr):
     check(lib().pd_decode(decoder._handle, host_in_ptr, dtype, B, host_out_ptr))
+
+
+def wave_frames(decoder, dtype):
+    """Frames one full wave of the persistent decode kernel holds (pd_wave_frames); 0 = CTA-per-frame kernel."""
+    return int(lib().pd_wave_frames(decoder._handle, dtype))
 
 
 def sync_check(decoder, stream=0):

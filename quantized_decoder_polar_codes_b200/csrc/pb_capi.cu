@@ -42,6 +42,9 @@ const void *path_fn_lloyd(int logL);
 constexpr int kOptlsMaxM = 1024;
 cudaError_t launch_optls(int n_problems, size_t smem, const double *density, const double *quanta, const int32_t *M, long long stride, int K,
                          double *out_density, double *out_quanta, int32_t *out_lut, double *T, int32_t *lm, long long t_stride, long long lm_stride);
+cudaError_t launch_mmi_table(int P, int M, int W, int mode, const double *p1, const double *p2, const double *l1, const double *l2,
+                             double c1, double c2, double *out1, double *out2);
+cudaError_t launch_mmi_dp(int P, int M, int K, int W, const double *T, int32_t *lm, int32_t *Az);
 const void *fast_kernel_fn(int logL, bool ca, bool fast) {
     if (logL >= 3) return fast ? scl_fn_l3_fast(ca) : scl_fn_l3_plain(ca);
     if (logL == 2) return scl_fn_l2(ca, fast);
@@ -369,7 +372,7 @@ size_t ws_need(const pd_decoder *D, int dtype, const void *d_in, int64_t B) {
 
 // frames one full wave of the chosen (persistent) kernel holds in flight; 0 for the CTA-per-frame generic kernel
 int64_t wave_frames(const pd_decoder *D, int dtype, const void *d_in) {
-    if (want_fast(D, dtype, d_in)) return (int64_t)D->sm_count * D->fast.ctas_per_sm * (32 >> D->fast.logL);
+    if (want_fast(D, dtype, d_in)) return (int64_t)D->sm_count * D->fast.ctas_per_sm * D->fast.p.warps * (32 >> D->fast.logL);
     if (want_path(D, dtype, d_in)) return (int64_t)D->sm_count * D->path.ctas_per_sm * (32 >> D->path.logL);
     return 0;
 }
@@ -523,6 +526,7 @@ int pd_create(const pd_config *c, pd_decoder **out) {
 }
 
 int pd_out_len(const pd_decoder *D) { return D ? D->dev.Kout : 0; }
+int64_t pd_wave_frames(const pd_decoder *D, int in_dtype) { return D ? wave_frames(D, in_dtype, nullptr) : 0; }
 int pd_code_len(const pd_decoder *D) { return D ? D->dev.N : 0; }
 const char *pd_kernel_name(const pd_decoder *D) { return D ? D->kernel_name : ""; }
 
@@ -554,7 +558,11 @@ int pd_decode_device(pd_decoder *D, const void *dev_in, int in_dtype, int64_t B,
     const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
     const int64_t wave = wave_frames(D, in_dtype, dev_in);
     constexpr int kSplit = 4;
-    const bool split = wave > 0 && B >= 8 * wave && ((N * esz) % 16 == 0);
+    // (Measured, round 2: also a batch of a whole number of waves gains 5 % from the split -- in one launch every warp of the
+    //  GPU walks the tree in the same phase, all forking or all streaming the big levels at once; overlapped launches are out
+    //  of phase and mix the pipes better.  POLAR_B200_FORCE_SPLIT=0/1 overrides.)
+    static const int force_split = getenv("POLAR_B200_FORCE_SPLIT") ? atoi(getenv("POLAR_B200_FORCE_SPLIT")) : -1;
+    const bool split = force_split == 0 ? false : (wave > 0 && B >= (force_split == 1 ? 4 : 8) * wave && ((N * esz) % 16 == 0));
     const int pieces = split ? kSplit : 1;
     const int64_t per = split ? (((B + kSplit - 1) / kSplit + 31) & ~(int64_t)31) : B;
     // workspace: one region per concurrently running piece
@@ -973,6 +981,74 @@ int pd_optls_quantize(const double *density, const double *quanta, const int32_t
     }
     cleanup();
     return rc;
+}
+
+// ---- lookup-table design, probability domain: the two device passes of the MMI quantizer (see pb_lutgen.cuh) --------
+}  // extern "C"
+namespace {
+struct DevBufs {
+    std::vector<void *> v;
+    ~DevBufs() { for (void *p : v) cudaFree(p); }
+    template <class T> T *get(size_t n) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        v.push_back(p);
+        return reinterpret_cast<T *>(p);
+    }
+};
+int mmi_check(const void *a, const void *b, int32_t P, int32_t M, int32_t K, int32_t device) {
+    if (!a || !b) return fail(PD_EINVAL, "null argument");
+    if (K < 2 || K > 64 || M < K || M > kOptlsMaxM) return fail(PD_EINVAL, "need 2 <= K <= 64 and K <= M <= %d (K=%d, M=%d)", kOptlsMaxM, K, M);
+    if ((long long)P * M * (M - K + 1) > (1ll << 27)) return fail(PD_EINVAL, "too many problems in one call (P*M*(M-K+1) <= 2^27)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PD_ECUDA, "no CUDA device: libpolar_b200 has no CPU path");
+    if (device < 0 || device >= ndev) return fail(PD_EINVAL, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    return PD_OK;
+}
+}  // namespace
+extern "C" {
+
+int pd_mmi_slice_sums(const double *p1, const double *p2, int32_t P, int32_t M, int32_t K, double *sum1, double *sum2, int32_t device) {
+    if (P <= 0) return PD_OK;
+    int rc = mmi_check(p1, p2, P, M, K, device);
+    if (rc) return rc;
+    if (!sum1 || !sum2) return fail(PD_EINVAL, "null argument");
+    const int W = M - K + 1;
+    const size_t nin = (size_t)P * M, nt = (size_t)P * M * W;
+    DevBufs b;
+    double *d1 = b.get<double>(nin), *d2 = b.get<double>(nin), *o1 = b.get<double>(nt), *o2 = b.get<double>(nt);
+    if (!d1 || !d2 || !o1 || !o2) return fail(PD_ENOMEM, "cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(d1, p1, nin * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d2, p2, nin * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(launch_mmi_table(P, M, W, 0, d1, d2, nullptr, nullptr, 0., 0., o1, o2));
+    g_launches++;
+    CUDA_TRY(cudaMemcpy(sum1, o1, nt * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(sum2, o2, nt * 8, cudaMemcpyDeviceToHost));
+    return PD_OK;
+}
+
+int pd_mmi_design(const double *p1, const double *p2, const double *l1, const double *l2, double c1, double c2,
+                  int32_t P, int32_t M, int32_t K, int32_t *Az, int32_t device) {
+    if (P <= 0) return PD_OK;
+    int rc = mmi_check(p1, p2, P, M, K, device);
+    if (rc) return rc;
+    if (!l1 || !l2 || !Az) return fail(PD_EINVAL, "null argument");
+    const int W = M - K + 1;
+    const size_t nin = (size_t)P * M, nt = (size_t)P * M * W;
+    DevBufs b;
+    double *d1 = b.get<double>(nin), *d2 = b.get<double>(nin), *e1 = b.get<double>(nt), *e2 = b.get<double>(nt), *T = b.get<double>(nt);
+    int32_t *lm = b.get<int32_t>((size_t)P * (K + 1) * W), *dAz = b.get<int32_t>((size_t)P * (K + 1));
+    if (!d1 || !d2 || !e1 || !e2 || !T || !lm || !dAz) return fail(PD_ENOMEM, "cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(d1, p1, nin * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d2, p2, nin * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e1, l1, nt * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e2, l2, nt * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(launch_mmi_table(P, M, W, 1, d1, d2, e1, e2, c1, c2, T, nullptr));
+    CUDA_TRY(launch_mmi_dp(P, M, K, W, T, lm, dAz));
+    g_launches += 2;
+    CUDA_TRY(cudaMemcpy(Az, dAz, (size_t)P * (K + 1) * 4, cudaMemcpyDeviceToHost));
+    return PD_OK;
 }
 
 #endif   // PB_HOST_EMU

@@ -127,4 +127,80 @@ optls_kernel(const double *__restrict__ density, const double *__restrict__ quan
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Probability-domain (maximum mutual information) quantizer design, the `MMIQuantizer.find_opt_quantizer` every node of
+// QuantizeDensityEvolution/QDensityEvolution_MMI.py:84,107 runs.  Followed bit for bit: the reference's numpy restatement
+// QuantizeDensityEvolution/MMIQuantizer.py (= MMQ below; the quantizer of record is C++ on OpenCV and cannot be built here).
+// Its cost table l(a',a) (MMQ:36-84) needs log2 of the cluster likelihoods; to stay identical with numpy the logarithms are
+// taken by numpy on the host between two passes of mmi_table_kernel:
+//   mode 0:  out1 = np.sum(p1[a':a]), out2 = np.sum(p2[a':a])                                         (MMQ:42-43)
+//   mode 1:  out1 = c1 * np.sum(p1[a':a] * l1) + c2 * np.sum(p2[a':a] * l2)   with l = log2(p) per entry  (MMQ:55-67)
+// both banded like T above (row a' holds a = a'+1 .. a'+W), one thread per entry, sums in numpy's pairwise order.
+__global__ void __launch_bounds__(256)
+mmi_table_kernel(const double *__restrict__ p1, const double *__restrict__ p2, int M, int W, int mode,
+                 const double *__restrict__ l1, const double *__restrict__ l2, double c1, double c2,
+                 double *__restrict__ out1, double *__restrict__ out2) {
+    const int p = blockIdx.y;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)M * W) return;
+    const double *q1 = p1 + (size_t)p * M, *q2 = p2 + (size_t)p * M;
+    const size_t o = (size_t)p * M * W + (size_t)e;
+    const int ap = (int)(e / W), a = ap + 1 + (int)(e % W);
+    if (a > M) { out1[o] = 0.; if (mode == 0) out2[o] = 0.; return; }
+    const int n = a - ap;
+    if (mode == 0) {
+        auto f1 = [&](int i) { return q1[i]; };
+        auto f2 = [&](int i) { return q2[i]; };
+        out1[o] = np_pairwise(f1, ap, n);
+        out2[o] = np_pairwise(f2, ap, n);
+    } else {
+        const double a1 = l1[o], a2 = l2[o];
+        auto f1 = [&](int i) { return q1[i] * a1; };
+        auto f2 = [&](int i) { return q2[i] * a2; };
+        const double s1 = np_pairwise(f1, ap, n), s2 = np_pairwise(f2, ap, n);
+        out1[o] = c1 * s1 + c2 * s2;
+    }
+}
+
+// The K-stage dynamic programme over cut positions (MMQ:175-207; maximisation, np.argmax = first maximum) and the
+// back-trace (MMQ:210-215).  One CTA per problem; Az[p][0..K] are the cluster boundaries in sorted order.
+__global__ void __launch_bounds__(256)
+mmi_dp_kernel(const double *__restrict__ Tall, int M, int K, int W, int32_t *__restrict__ ws_lm, int32_t *__restrict__ Az_out) {
+    extern __shared__ double sm_d[];
+    const int p = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+    const double *T = Tall + (size_t)p * M * W;
+    int32_t *lm = ws_lm + (size_t)p * (K + 1) * W;
+    double *col0 = sm_d, *col1 = sm_d + W;
+    for (int i = tid; i < W; i += nth) col0[i] = T[i];          // state[:,1] = table[0, 1 .. W]
+    __syncthreads();
+    double *prev = col0, *cur = col1;
+    for (int z = 2; z <= K; ++z) {
+        const int a_lo = z < K ? z : M, cnt = z < K ? W : 1;
+        for (int r = tid; r < cnt; r += nth) {
+            const int a = a_lo + r;
+            int best_ap = z - 1;
+            double best = prev[0] + T[(size_t)(z - 1) * W + (a - z)];
+            for (int ap = z; ap <= a - 1; ++ap) {
+                const double v = prev[ap - (z - 1)] + T[(size_t)ap * W + (a - ap - 1)];
+                if (v > best) { best = v; best_ap = ap; }
+            }
+            const int row = z < K ? r : W - 1;
+            cur[row] = best;
+            lm[(size_t)z * W + row] = best_ap;
+        }
+        __syncthreads();
+        double *t = prev; prev = cur; cur = t;
+    }
+    if (tid == 0) {
+        int32_t *Az = Az_out + (size_t)p * (K + 1);
+        Az[0] = 0;
+        Az[K] = M;
+        if (K >= 2) {
+            int opt = lm[(size_t)K * W + (W - 1)];
+            Az[K - 1] = opt;
+            for (int z = K - 1; z >= 2; --z) { opt = lm[(size_t)z * W + (opt - z)]; Az[z - 1] = opt; }
+        }
+    }
+}
+
 }  // namespace pb

@@ -39,7 +39,13 @@
 
 namespace pb {
 
-constexpr int kRingChunks = 4;     // ring slots per lane, 4 lines (16 bytes per lane) each; 3 chunks in flight
+// Table stream ring, one per CTA, filled by the producer warp with TMA bulk copies (cp.async.bulk + mbarrier):
+// kStages stages of kCPS chunks (512 bytes = 4 table lines, lane-transposed) each.
+constexpr int kStages = 4;
+constexpr int kCPS = 4;
+constexpr int kRingSlots = kStages * kCPS;          // chunks in the ring
+constexpr unsigned kStageBytes = kCPS * 512u;
+constexpr int kMaxWarps = 4;                         // consumer warps per CTA (+ 1 producer warp)
 constexpr unsigned kFull = 0xffffffffu;
 
 enum FastOp : uint32_t {
@@ -58,6 +64,8 @@ struct FastParams {
     int r1_words;                  // shared-memory words for the R1 scratch (0 when the code has no R1 node)
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
+    int warps;                     // consumer warps per CTA; one more warp streams the tables
+    int warp_words;                // shared-memory words of one consumer warp (its V, X, scratch, fork cells)
     int vwords, xwords, scrwords;  // shared-memory words per lane: value levels gl+1..top, X; scratch words per warp
     int scr_off;                   // word offset of the epilogue scratch: its own region, or 0 = on top of the (then dead) value levels
     int gl;                        // value levels 1..gl live in the global (L2-resident) workspace, the rest in shared memory
@@ -82,22 +90,40 @@ struct FastPlan {
 // pointer value in the host emulation (tools/emu)
 #ifdef PB_HOST_EMU
 using smaddr_t = size_t;
-__device__ __forceinline__ void ldgsts16(smaddr_t dst, const void *gsrc) { memcpy(reinterpret_cast<void *>(dst), gsrc, 16); }
-template <int NPEND> __device__ __forceinline__ void cp_async_wait() {}
 __device__ __forceinline__ uint4 lds128(smaddr_t a) { uint4 v; memcpy(&v, reinterpret_cast<const void *>(a), 16); return v; }
+// mbarrier: {arrivals still pending, arrivals per phase, completed phases}
+struct EmuBar { uint16_t pending, count; uint32_t phases; };
+__device__ __forceinline__ void mbar_init(smaddr_t b, unsigned count) { *reinterpret_cast<EmuBar *>(b) = EmuBar{(uint16_t)count, (uint16_t)count, 0u}; }
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_arrive(smaddr_t b) {
+    EmuBar *m = reinterpret_cast<EmuBar *>(b);
+    if (--m->pending == 0) { m->pending = m->count; m->phases++; }
+}
+__device__ __forceinline__ void mbar_wait(smaddr_t b, unsigned parity) {   // returns once the phase of that parity is complete
+    while ((reinterpret_cast<EmuBar *>(b)->phases & 1u) == parity) pb_emu::yield();
+}
+__device__ __forceinline__ void bulk_load(smaddr_t dst, const void *gsrc, unsigned bytes, smaddr_t bar) {
+    memcpy(reinterpret_cast<void *>(dst), gsrc, bytes);
+    mbar_arrive(bar);
+}
 #else
 using smaddr_t = unsigned;
-__device__ __forceinline__ void ldgsts16(smaddr_t dst, const void *gsrc) {   // one committed cp.async group of 16 bytes
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(dst), "l"(gsrc));
-}
-template <int NPEND>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory");
-}
 __device__ __forceinline__ uint4 lds128(smaddr_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
+}
+__device__ __forceinline__ void mbar_init(smaddr_t b, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(count)); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(smaddr_t b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory"); }
+__device__ __forceinline__ void mbar_wait(smaddr_t b, unsigned parity) {   // returns once the phase of that parity is complete
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+                 ::"r"(b), "r"(parity) : "memory");
+}
+// one TMA bulk copy global -> shared; `bar` receives the single arrival and the byte count
+__device__ __forceinline__ void bulk_load(smaddr_t dst, const void *gsrc, unsigned bytes, smaddr_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
 }
 #endif
 
@@ -114,37 +140,31 @@ struct R1Less {
 };
 static __device__ __noinline__ void sort_r1_packed(unsigned short *col, int n) { std_sort_acc<16>(R1Acc{col}, n, R1Less{}); }
 
-struct RingState {
-    unsigned fetch_off;   // byte offset (within the stream) of the next chunk to prefetch
-    unsigned chunk_no;    // chunks consumed so far
-};
-__device__ __forceinline__ void ring_issue(RingState &rs, unsigned slot, smaddr_t ring_lane, const char *stream_lane, unsigned stream_bytes) {
-    ldgsts16(ring_lane + slot * 512u, stream_lane + rs.fetch_off);
-    rs.fetch_off += 512u;
-    if (rs.fetch_off == stream_bytes) rs.fetch_off = 0;
+// Consumer side of the stream ring.  `cc` counts the chunks this warp has consumed since the kernel started; the ring slot,
+// the stage and the barrier phase follow from it.  The first chunk of a stage waits for the stage's "full" barrier, the last
+// one hands the stage back ("empty", one arrival per consumer warp).
+__device__ __forceinline__ uint4 ring_next_chunk(uint32_t &cc, smaddr_t ring_lane, smaddr_t bars, int lane) {
+    const uint32_t slot = cc & (kRingSlots - 1), st = slot / kCPS;
+    if ((cc & (kCPS - 1)) == 0) mbar_wait(bars + st * 8u, (cc / kRingSlots) & 1u);
+    const uint4 v = lds128(ring_lane + slot * 512u);
+    if ((cc & (kCPS - 1)) == kCPS - 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + (kStages + st) * 8u);
+    }
+    ++cc;
+    return v;
 }
-__device__ __forceinline__ uint4 ring_next_chunk(RingState &rs, smaddr_t ring_lane, const char *stream_lane, unsigned stream_bytes) {
-    const unsigned slot = rs.chunk_no & (kRingChunks - 1);
-    ring_issue(rs, (slot + kRingChunks - 1) & (kRingChunks - 1), ring_lane, stream_lane, stream_bytes);   // refill the slot consumed before
-    cp_async_wait<kRingChunks - 1>();                                                                     // ... and make sure this chunk has landed
-    ++rs.chunk_no;
-    return lds128(ring_lane + slot * 512u);
-}
-// out-of-line refill for the Fast-SSC variant (~40 consumption sites): everything travels in registers, the caller
-// advances the ring state itself
-static __device__ __noinline__ uint4 ring_fetch_outlined(unsigned fetch_off, unsigned chunk_no, smaddr_t ring_lane, const char *stream_lane) {
-    const unsigned slot = chunk_no & (kRingChunks - 1);
-    ldgsts16(ring_lane + ((slot + kRingChunks - 1) & (kRingChunks - 1)) * 512u, stream_lane + fetch_off);
-    cp_async_wait<kRingChunks - 1>();
-    return lds128(ring_lane + slot * 512u);
+// out-of-line variant for the Fast-SSC kernels (~40 consumption sites)
+static __device__ __noinline__ uint4 ring_fetch_outlined(uint32_t cc, smaddr_t ring_lane, smaddr_t bars, int lane) {
+    return ring_next_chunk(cc, ring_lane, bars, lane);
 }
 struct LineState {
-    RingState rs;
-    uint4 cur;   // the chunk lines are currently taken from
-    int q;       // next line inside `cur` (4 = exhausted)
+    uint32_t cc;   // chunks consumed so far
+    uint4 cur;     // the chunk lines are currently taken from
+    int q;         // next line inside `cur` (4 = exhausted)
 };
-__device__ __forceinline__ uint32_t next_line_inl(LineState &ls, smaddr_t ring_lane, const char *stream_lane, unsigned stream_bytes) {
-    if (ls.q == 4) { ls.cur = ring_next_chunk(ls.rs, ring_lane, stream_lane, stream_bytes); ls.q = 0; }
+__device__ __forceinline__ uint32_t next_line_inl(LineState &ls, smaddr_t ring_lane, smaddr_t bars, int lane) {
+    if (ls.q == 4) { ls.cur = ring_next_chunk(ls.cc, ring_lane, bars, lane); ls.q = 0; }
     const uint32_t v = ls.q == 0 ? ls.cur.x : ls.q == 1 ? ls.cur.y : ls.q == 2 ? ls.cur.z : ls.cur.w;
     ++ls.q;
     return v;
@@ -155,51 +175,78 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x) {
     return (x & 0xfu) | ((x >> 4) & 0xf0u) | ((x >> 8) & 0xf00u) | ((x >> 12) & 0xf000u);
 }
 
-// (register budget left to ptxas: 64 for the plain variants, 80 for the Fast ones; forcing 96 / 64 measured slower)
+// One CTA = fp.warps consumer warps, each decoding its own frame groups, + one producer warp that streams the tables
+// (6 CTAs of 4+1 warps per SM at N=1024, L=8 = 24 decoding warps: 64 registers per thread at most; the Fast variants, which
+// live with fewer resident warps, may take 96).
 template <int LOGL, bool CA, bool FAST>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__((kMaxWarps + 1) * 32, FAST ? 4 : 6)
 scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastParams fp, const void *__restrict__ in, int in_dtype,
                     uint8_t *__restrict__ out, long long B, uint32_t *__restrict__ ws, int *err_flag, double *dbg_pm, int *dbg_win) {
     constexpr int L = 1 << LOGL;
     constexpr int FPW = 32 / L;
     PB_DYN_SMEM(uint32_t, sm);
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, W = fp.warps;
+    const int wid = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);   // (read through a shuffle: the compiler then treats it as warp-uniform)
     const int grp = lane >> LOGL, me = lane & (L - 1), gbase = lane & ~(L - 1);
     const int N = d.N, n = d.n;
     const int top = n - 3;          // depth of the subtree roots = deepest value level kept in memory
 
-    uint32_t *V = sm;                                  // value levels gl+1..top, [word][lane]
+    // ---- table stream.  Every f/g table (one 128-byte line = 16x16 nibbles) and every leaf LLR row (16 doubles) is
+    //      consumed exactly once per pass, in a fixed order, the same for every warp, and lane l only ever needs word l of
+    //      a line.  The host lays the lines out in consumption order, 4 lines per lane-transposed 512-byte chunk; the
+    //      producer warp moves them stage by stage into the CTA's ring with TMA bulk copies, the consumer warps read their
+    //      16 bytes per chunk with one LDS.128.  full[s] / empty[s] mbarriers carry the hand-over. ----
+    uint32_t *RINGB = sm + (size_t)W * fp.warp_words;
+    const smaddr_t ring0 = (smaddr_t)__cvta_generic_to_shared(RINGB);
+    const smaddr_t bars = ring0 + kRingSlots * 512u;          // full[kStages], empty[kStages]
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(bars + i * 8u, 1u); mbar_init(bars + (kStages + i) * 8u, (unsigned)W); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // static schedule: in pass p, warp w of CTA b decodes frame group (p * gridDim.x + b) * W + w; a CTA runs as many
+    // passes as its warp 0 has groups (warps without a group still drain the stream)
+    const long long n_groups = (B + FPW - 1) / FPW;
+    const long long per_pass = (long long)gridDim.x * W;
+    const long long first = (long long)blockIdx.x * W;
+    const int n_pass = first < n_groups ? (int)((n_groups - first + per_pass - 1) / per_pass) : 0;
+    const uint32_t spp = (uint32_t)fp.n_chunks / kCPS;        // stages per pass (the stream is padded to whole stages)
+    if (wid == W) {                                           // ---- producer warp
+        if (lane == 0) {
+            const char *src = reinterpret_cast<const char *>(fp.stream);
+            uint32_t i = 0;
+            for (int p = 0; p < n_pass; ++p)
+                for (uint32_t s = 0; s < spp; ++s, ++i) {
+                    const uint32_t st = i & (kStages - 1);
+                    mbar_wait(bars + (kStages + st) * 8u, ((i / kStages) & 1u) ^ 1u);     // slot free (passes at once the first time round)
+                    bulk_load(ring0 + st * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bars + st * 8u);
+                }
+        }
+        return;
+    }
+
+    uint32_t *V = sm + (size_t)wid * fp.warp_words;    // value levels gl+1..top, [word][lane]
     uint32_t *X = V + fp.vwords * 32;                  // partial sums, in place, [word][lane]
-    uint32_t *SCR = sm + fp.scr_off;                   // epilogue scratch [word][frame in warp] (L > 1)
-    uint32_t *RING = X + fp.xwords * 32 + fp.scrwords; // [kRingChunks][lane][4]
-    uint32_t *G = ws + (size_t)blockIdx.x * fp.gwords * 32;   // value levels 1..gl, [word][lane], L2-resident
-    double *KS = reinterpret_cast<double *>(RING + kRingChunks * 128);   // key pairs (keep, flip), [path][frame in warp][2]: the FPW groups read adjacent 16-byte cells
+    uint32_t *SCR = V + fp.scr_off;                    // epilogue scratch [word][frame in warp] (L > 1)
+    double *KS = reinterpret_cast<double *>(X + fp.xwords * 32 + fp.scrwords);   // key pairs (keep, flip), [path][frame in warp][2]: the FPW groups read adjacent 16-byte cells
     uint32_t *SEL = reinterpret_cast<uint32_t *>(KS + 64);               // [32]
     double *R1S = reinterpret_cast<double *>(SEL + 32);                  // [7][32] smallest |llr| of an R1 node (Fast kinds)
     uint32_t *R1Q = reinterpret_cast<uint32_t *>(R1S + 7 * 32);          // [7][32] their positions
     unsigned short *R1P = reinterpret_cast<unsigned short *>(R1S);       // [32][32] packed sort keys of an R1 node (dead before R1S/R1Q are written)
+    uint32_t *G = ws + ((size_t)blockIdx.x * W + wid) * fp.gwords * 32;  // value levels 1..gl, [word][lane], L2-resident
 
-    // ---- table stream.  Every f/g table (one 128-byte line = 16x16 nibbles) and every leaf LLR row (16 doubles)
-    //      is consumed exactly once per pass, in a fixed order, and lane l only ever needs word l of a line.  The
-    //      host lays the lines out in consumption order, 4 lines per lane-transposed 512-byte chunk, and each
-    //      lane streams ITS 16 bytes of every chunk with cp.async into a private ring (no cross-lane sync). ----
     LineState ls;
-    ls.rs.fetch_off = 0u; ls.rs.chunk_no = 0u; ls.cur = make_uint4(0, 0, 0, 0); ls.q = 4;
-    const unsigned stream_bytes = (unsigned)fp.n_chunks * 512u;
-    const char *stream_lane = reinterpret_cast<const char *>(fp.stream) + lane * 16;
-    const smaddr_t ring_lane = (smaddr_t)__cvta_generic_to_shared(RING + lane * 4);   // this lane's 16 bytes of slot 0
-    for (int i = 0; i < kRingChunks - 1; ++i) ring_issue(ls.rs, i, ring_lane, stream_lane, stream_bytes);
+    ls.cc = 0u; ls.cur = make_uint4(0, 0, 0, 0); ls.q = 4;
+    const smaddr_t ring_lane = ring0 + (unsigned)lane * 16u;   // this lane's 16 bytes of slot 0
     // the Fast-SSC variant has ~40 consumption sites: there the stream accessors are real (out-of-line) functions so
     // that the hot code stays inside the instruction cache; the plain variant inlines them
     auto next_chunk = [&]() -> uint4 {
         if (FAST && L > 1) {
-            const uint4 v = ring_fetch_outlined(ls.rs.fetch_off, ls.rs.chunk_no, ring_lane, stream_lane);
-            ls.rs.fetch_off += 512u;
-            if (ls.rs.fetch_off == stream_bytes) ls.rs.fetch_off = 0;
-            ++ls.rs.chunk_no;
+            const uint4 v = ring_fetch_outlined(ls.cc, ring_lane, bars, lane);
+            ++ls.cc;
             return v;
         }
-        return ring_next_chunk(ls.rs, ring_lane, stream_lane, stream_bytes);
+        return ring_next_chunk(ls.cc, ring_lane, bars, lane);
     };
     // upper-level steps and special nodes take their lines one at a time out of the current chunk.  In the Fast-SSC
     // variant `cur` is a queue with the next line in .x (no selects at the many call sites)
@@ -211,7 +258,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             ++ls.q;
             return v;
         }
-        return next_line_inl(ls, ring_lane, stream_lane, stream_bytes);
+        return next_line_inl(ls, ring_lane, bars, lane);
     };
     // eight f (or g) lookups for one word of symbols: out nibble k = T[u_k][a_k][b_k] with a_k / b_k nibble k of A / Bv.
     // Even and odd nibbles are split into byte lanes so that shuffle sources (a*2 + b>>3) and nibble shifts ((b&7)*4)
@@ -248,8 +295,18 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     };
     auto nib = [](uint32_t w, int k) -> uint32_t { return (w >> (4 * k)) & 15u; };
 
-    const long long n_groups = (B + FPW - 1) / FPW;
-    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const long long g = ((long long)pass * gridDim.x + blockIdx.x) * W + wid;
+        if (g >= n_groups) {   // no group left for this warp: hand the pass's stages straight back
+            for (uint32_t s2 = 0; s2 < spp; ++s2, ls.cc += kCPS) {
+                const uint32_t st = (ls.cc & (kRingSlots - 1)) / kCPS;
+                mbar_wait(bars + st * 8u, (ls.cc / kRingSlots) & 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + (kStages + st) * 8u);
+            }
+            continue;
+        }
+        const uint32_t cc_pass = ls.cc;
         long long my_frame = g * FPW + grp;
         if (my_frame >= B) my_frame = B - 1;
         // 8 channel symbols (one output word's worth of the a- or b-half) -> 8 nibbles, with the range check the
@@ -320,25 +377,47 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 __syncwarp();
                 return;
             }
-            uint32_t *dst = level_ptr(dd + 1, lane);
-            const uint32_t *xsrc = X + uslot(dd + 1);
-            const uint32_t ub0 = (2u * node) * (uint32_t)ct;
+            // One instance of the word loop per (source, destination) memory space -- workspace (global, L2) or shared --
+            // so that every access is a plain LDG/STG or LDS/STS with a running offset.  Operands of word w+1 are fetched
+            // while word w is looked up; the u bits of a g step come 32 at a time out of the partial-sum column.
             const int nw = ct >> 3;
-            auto getA = [&](int w) -> uint32_t { return src[w * sstride]; };
-            auto getB = [&](int w) -> uint32_t { return src[(nw + w) * sstride]; };
-            auto getU = [&](int w) -> uint32_t {
-                if (!isg) return 0u;
-                const uint32_t bit = ub0 + 8u * w;
-                return xsrc[(bit >> 5) * 32] >> (bit & 31u);
+            const uint32_t ub0 = (2u * node) * (uint32_t)ct;
+            const int so = (dd == 0) ? grp : fp.voff[dd] * 32 + vslot(dd);
+            const int dof = fp.voff[dd + 1] * 32 + lane;
+            const int xo_ = (int)(ub0 >> 5) * 32 + uslot(dd + 1);
+            const int ush = (int)(ub0 & 31u);
+            auto body = [&](auto sg_c, auto dg_c, auto isg_c) {
+                constexpr bool SG = decltype(sg_c)::value, DG = decltype(dg_c)::value, ISG = decltype(isg_c)::value;
+                const uint32_t *pa = (SG ? G : V) + so;
+                const uint32_t *pb = pa + nw * sstride;
+                uint32_t *pd = (DG ? G : V) + dof;
+                const uint32_t *px = X + xo_;
+                uint32_t A = *pa, Bv = *pb, xw = 0;
+                if (ISG) xw = *px >> ush;
+                for (int w = 0; w < nw; ++w) {
+                    uint32_t An = 0, Bn = 0;
+                    if (w + 1 < nw) { pa += sstride; pb += sstride; An = *pa; Bn = *pb; }
+                    const uint32_t o = lookup8(A, Bv, xw, t0, t1, isg_c);
+                    *pd = o;
+                    pd += 32;
+                    A = An; Bv = Bn;
+                    if (ISG) {
+                        xw >>= 8;
+                        if ((w & 3) == 3 && w + 1 < nw) { px += 32; xw = *px; }
+                    }
+                }
             };
-            // operands of word w+1 are fetched (possibly from L2) while word w is looked up
-            uint32_t A = getA(0), Bv = getB(0), ub = getU(0);
-            for (int w = 0; w < nw; ++w) {
-                uint32_t An = 0, Bn = 0, un = 0;
-                if (w + 1 < nw) { An = getA(w + 1); Bn = getB(w + 1); un = getU(w + 1); }
-                const uint32_t o = isg ? lookup8(A, Bv, ub, t0, t1, std::true_type{}) : lookup8(A, Bv, 0u, t0, t0, std::false_type{});
-                dst[w * 32] = o;
-                A = An; Bv = Bn; ub = un;
+            const bool sg = dd <= fp.gl, dg = dd + 1 <= fp.gl;   // (dd == 0: the packed channel words live in the workspace too)
+            using T_ = std::true_type;
+            using F_ = std::false_type;
+            if (isg) {
+                if (dg) body(T_{}, T_{}, T_{});
+                else if (sg) body(T_{}, F_{}, T_{});
+                else body(F_{}, F_{}, T_{});
+            } else {
+                if (dg) body(T_{}, T_{}, F_{});
+                else if (sg) body(T_{}, F_{}, F_{});
+                else body(F_{}, F_{}, F_{});
             }
             if (L > 1) setown(pv, dd + 1);
             __syncwarp();
@@ -428,8 +507,9 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             pv = __shfl_sync(kFull, pv, p);
             pu = __shfl_sync(kFull, pu, p);
         };
+        // LLR line: lane s holds the low word of entry s, lane 16+s its high word (sym < 16)
         auto llr_of = [&](uint32_t lr, uint32_t sym) -> double {
-            const int lo_ = __shfl_sync(kFull, (int)lr, 2 * sym), hi_ = __shfl_sync(kFull, (int)lr, 2 * sym + 1);
+            const int lo_ = __shfl_sync(kFull, (int)lr, (int)sym), hi_ = __shfl_sync(kFull, (int)lr, (int)(sym + 16u));
             return __hiloint2double(hi_, lo_);
         };
         // result bits of a node at (dd,node) with `temp` <= 32 leaves -> in place (subtree register or own X slot)
@@ -672,69 +752,79 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 __syncwarp();
                 break;
             }
-            case FOP_SUB8:       // a whole plain 8-leaf subtree: 8 chunk-aligned chunks, see plan_fast_lut
-            case FOP_SPAIR: {    // one leaf pair of a subtree that contains special nodes: 5 lines
-                const bool whole = !FAST || ot == FOP_SUB8;
-                const int s = whole ? (int)onode : (int)(onode >> 2);
+            case FOP_SUB8: {     // a whole plain 8-leaf subtree: 8 chunk-aligned chunks, see plan_fast_lut
+                // Symbols travel as PAIR BYTES p = a | b << 4 (the two operands of one lookup): the table word is lane
+                // a*2 + (b>>3) = ((p&15)<<1) | (p>>7), the nibble shift (b&7)*4 = (p>>2) & 0x1c -- for four pairs at once with
+                // byte-lane arithmetic.  w3 = 4 pair bytes of the subtree root, w21 = [15:0] 2 pair bytes of the depth
+                // top+1 node, [23:16] the pair byte of the depth top+2 node, xb = partial sums in place.
+                const int s = (int)onode;
                 const uint32_t fz = (__ldg(fp.frozen_words + (s >> 2)) >> ((s & 3) * 8)) & 0xffu;
-                if (whole) { ls.q = 4; w3 = *level_ptr(top, vslot(top)); xb = 0; }
-                const int c4_end = whole ? 4 : (int)(onode & 3u) + 1;
+                ls.q = 4;
+                {
+                    const uint32_t w = *level_ptr(top, vslot(top));   // nibbles a0..a3 b0..b3
+                    uint32_t lo = w & 0xffffu, hi = w >> 16;
+                    lo = (lo | (lo << 8)) & 0x00ff00ffu; lo = (lo | (lo << 4)) & 0x0f0f0f0fu;
+                    hi = (hi | (hi << 8)) & 0x00ff00ffu; hi = (hi | (hi << 4)) & 0x0f0f0f0fu;
+                    w3 = lo | (hi << 4);
+                }
+                xb = 0;
+                auto pb_lane = [](uint32_t P) -> uint32_t { return ((P & 0x0f0f0f0fu) << 1) | ((P >> 7) & 0x01010101u); };
+                auto pb_amt = [](uint32_t P) -> uint32_t { return (P >> 2) & 0x1c1c1c1cu; };
 #pragma unroll 1
-                for (int c4 = whole ? 0 : (int)(onode & 3u); c4 < c4_end; ++c4) {
+                for (int c4 = 0; c4 < 4; ++c4) {
                     const int pos = 2 * c4;
-                    uint4 c0, c1;
-                    if (whole) {
-                        c0 = next_chunk(); c1 = next_chunk();
-                        if ((c4 & 1) == 0) {
-                            uint32_t w2 = 0;
-                            if (c4 == 0) {          // A.f
+                    const uint4 c0 = next_chunk(), c1 = next_chunk();
+                    if ((c4 & 1) == 0) {
+                        // depth top node: four lookups, f (c4 == 0) or g with u = partial sums 0..3 of the left half
+                        const uint32_t S = pb_lane(w3), H = pb_amt(w3);
+                        uint32_t R = 0;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) w2 |= lut16(c0.x, nib(w3, k), nib(w3, k + 4)) << (4 * k);
-                            } else {                // A.g
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint32_t a = nib(w3, k), b = nib(w3, k + 4);
-                                    const uint32_t s0 = lut16(c0.x, a, b), s1 = lut16(c0.y, a, b);
-                                    w2 |= (((xb >> k) & 1u) ? s1 : s0) << (4 * k);
-                                }
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t sel = k == 0 ? 0x3214u : k == 1 ? 0x3240u : k == 2 ? 0x3410u : 0x4210u;
+                            uint32_t wv = __shfl_sync(kFull, c0.x, (int)(S >> (8 * k)));
+                            if (c4 != 0) {
+                                const uint32_t w1v = __shfl_sync(kFull, c0.y, (int)(S >> (8 * k)));
+                                wv = ((xb >> k) & 1u) ? w1v : wv;
                             }
-                            const uint32_t w1 = lut16(c0.z, nib(w2, 0), nib(w2, 2)) | (lut16(c0.z, nib(w2, 1), nib(w2, 3)) << 4);   // B.f
-                            w21 = w2 | (w1 << 16);
-                        } else {                    // B.g
-                            const uint32_t c2 = w21 & 0xffffu;
-                            uint32_t w1 = 0;
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                const uint32_t a = nib(c2, k), b = nib(c2, k + 2);
-                                const uint32_t s0 = lut16(c0.x, a, b), s1 = lut16(c0.y, a, b);
-                                w1 |= (((xb >> (pos - 2 + k)) & 1u) ? s1 : s0) << (4 * k);
-                            }
-                            w21 = c2 | (w1 << 16);
+                            R = __byte_perm(R, __funnelshift_r(wv, 0u, H >> (8 * k)), sel);
                         }
+                        R &= 0x0f0f0f0fu;                                   // o0 o1 o2 o3, one per byte
+                        const uint32_t w2p = (R | (R >> 12)) & 0xffffu;     // pair bytes (o0,o2) (o1,o3) of the left / right child
+                        // depth top+1 node, f
+                        const uint32_t S2 = pb_lane(w2p), H2 = pb_amt(w2p);
+                        const uint32_t r0 = __funnelshift_r(__shfl_sync(kFull, c0.z, (int)S2), 0u, H2);
+                        const uint32_t r1 = __funnelshift_r(__shfl_sync(kFull, c0.z, (int)(S2 >> 8)), 0u, H2 >> 8);
+                        w21 = w2p | ((r0 & 15u) << 16) | ((r1 & 15u) << 20);
                     } else {
-                        c0.x = c0.y = c0.z = 0;
-                        c0.w = next_line();
-                        c1.x = next_line(); c1.y = next_line(); c1.z = next_line(); c1.w = next_line();
+                        // depth top+1 node, g with u = the two partial sums of its left child
+                        const uint32_t w2p = w21 & 0xffffu;
+                        const uint32_t S2 = pb_lane(w2p), H2 = pb_amt(w2p);
+                        const uint32_t a0 = __shfl_sync(kFull, c0.x, (int)S2), a1 = __shfl_sync(kFull, c0.y, (int)S2);
+                        const uint32_t b0 = __shfl_sync(kFull, c0.x, (int)(S2 >> 8)), b1 = __shfl_sync(kFull, c0.y, (int)(S2 >> 8));
+                        const uint32_t r0 = __funnelshift_r(((xb >> (pos - 2)) & 1u) ? a1 : a0, 0u, H2);
+                        const uint32_t r1 = __funnelshift_r(((xb >> (pos - 1)) & 1u) ? b1 : b0, 0u, H2 >> 8);
+                        w21 = w2p | ((r0 & 15u) << 16) | ((r1 & 15u) << 20);
                     }
-#pragma unroll 1
+#pragma unroll
                     for (int side = 0; side < 2; ++side) {
                         // leaf symbol through the depth n-1 node: f table (left leaf) or g tables with u = left leaf's bit
-                        const uint32_t w1 = w21 >> 16;
-                        const uint32_t a = nib(w1, 0), b = nib(w1, 1);
-                        uint32_t sym;
+                        const uint32_t cp = w21 >> 16;
+                        const int cl = (int)(((cp & 15u) << 1) | (cp >> 7));
+                        const uint32_t ca_ = (cp >> 2) & 0x1cu;
+                        uint32_t wv;
                         if (side == 0) {
-                            sym = lut16(c0.w, a, b);
+                            wv = __shfl_sync(kFull, c0.w, cl);
                         } else {
-                            const uint32_t s0 = lut16(c1.y, a, b), s1 = lut16(c1.z, a, b);
-                            sym = ((xb >> pos) & 1u) ? s1 : s0;
+                            const uint32_t s0 = __shfl_sync(kFull, c1.y, cl), s1 = __shfl_sync(kFull, c1.z, cl);
+                            wv = ((xb >> pos) & 1u) ? s1 : s0;
                         }
+                        const uint32_t sym = (wv >> ca_) & 15u;
                         const int lp = pos + side;
                         const bool frozen = (fz >> lp) & 1u;
                         // leaf decision (PD/src/SCLUTDecoder.cpp:59-67 / SCLLUTDecoder.cpp:92-145)
                         const double DM = llr_of(side == 0 ? c1.x : c1.w, sym);
-                        uint32_t bit = 0;
                         if (L == 1) {
-                            bit = (!frozen && DM <= 0) ? 1u : 0u;
+                            if (!frozen && DM <= 0) xb |= 1u << lp;
                         } else if (frozen) {
                             if (DM < 0) PM += fabs(DM);
                         } else {
@@ -742,21 +832,57 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                             int p;
                             uint32_t fl;
                             fork(PM, PM + fabs(DM), p, fl);
-                            bit = __shfl_sync(kFull, dec, p) ^ fl;
+                            xb |= (__shfl_sync(kFull, dec, p) ^ fl) << lp;
                         }
-                        xb = (xb & ~(1u << lp)) | (bit << lp);
                     }
-                    xb ^= ((xb >> (pos + 1)) & 1u) << pos;                          // combine of the depth n-1 node
-                    if (whole && (c4 & 1)) xb ^= ((xb >> pos) & 3u) << (pos - 2);   // combine of the depth n-2 node
+                    xb ^= ((xb >> (pos + 1)) & 1u) << pos;                 // combine of the depth n-1 node
+                    if (c4 & 1) xb ^= ((xb >> pos) & 3u) << (pos - 2);     // combine of the depth n-2 node
                 }
-                if (whole) {
-                    xb ^= (xb >> 4) & 15u;                                          // combine of the subtree root
-                    uint32_t *xo = X + ((8u * s) >> 5) * 32 + lane;
-                    const int sh = (8 * s) & 31;
-                    *xo = (*xo & ~(0xffu << sh)) | ((xb & 0xffu) << sh);
-                    if (L > 1 && (s & 1) == 0) setown(pu, top);
-                    __syncwarp();
+                xb ^= (xb >> 4) & 15u;                                     // combine of the subtree root
+                uint32_t *xo = X + ((8u * s) >> 5) * 32 + lane;
+                const int sh = (8 * s) & 31;
+                *xo = (*xo & ~(0xffu << sh)) | ((xb & 0xffu) << sh);
+                if (L > 1 && (s & 1) == 0) setown(pu, top);
+                __syncwarp();
+                break;
+            }
+            case FOP_SPAIR: if (FAST) {    // one leaf pair of a subtree that contains special nodes: 5 lines
+                const int s = (int)(onode >> 2);
+                const uint32_t fz = (__ldg(fp.frozen_words + (s >> 2)) >> ((s & 3) * 8)) & 0xffu;
+                const int c4 = (int)(onode & 3u), pos = 2 * c4;
+                uint4 c0, c1;
+                c0.x = c0.y = c0.z = 0;
+                c0.w = next_line();
+                c1.x = next_line(); c1.y = next_line(); c1.z = next_line(); c1.w = next_line();
+#pragma unroll 1
+                for (int side = 0; side < 2; ++side) {
+                    const uint32_t w1 = w21 >> 16;
+                    const uint32_t a = nib(w1, 0), b = nib(w1, 1);
+                    uint32_t sym;
+                    if (side == 0) {
+                        sym = lut16(c0.w, a, b);
+                    } else {
+                        const uint32_t s0 = lut16(c1.y, a, b), s1 = lut16(c1.z, a, b);
+                        sym = ((xb >> pos) & 1u) ? s1 : s0;
+                    }
+                    const int lp = pos + side;
+                    const bool frozen = (fz >> lp) & 1u;
+                    const double DM = llr_of(side == 0 ? c1.x : c1.w, sym);
+                    uint32_t bit = 0;
+                    if (L == 1) {
+                        bit = (!frozen && DM <= 0) ? 1u : 0u;
+                    } else if (frozen) {
+                        if (DM < 0) PM += fabs(DM);
+                    } else {
+                        const uint32_t dec = (DM < 0) ? 1u : 0u;
+                        int p;
+                        uint32_t fl;
+                        fork(PM, PM + fabs(DM), p, fl);
+                        bit = __shfl_sync(kFull, dec, p) ^ fl;
+                    }
+                    xb = (xb & ~(1u << lp)) | (bit << lp);
                 }
+                xb ^= ((xb >> (pos + 1)) & 1u) << pos;                          // combine of the depth n-1 node
                 break;
             }
             default: break;
@@ -838,8 +964,17 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             }
         }
         __syncwarp();
+        // hand back a partly consumed last stage; the next pass starts on the next stage
+        if (ls.cc & (kCPS - 1)) {
+            if (lane == 0) mbar_arrive(bars + (kStages + (ls.cc & (kRingSlots - 1)) / kCPS) * 8u);
+            ls.cc = (ls.cc + kCPS - 1) & ~(uint32_t)(kCPS - 1);
+        }
+#ifdef PB_HOST_EMU
+        if (ls.cc - cc_pass != spp * kCPS) { fprintf(stderr, "scl_lut_warp: pass consumed %u chunks, stream has %u\n", ls.cc - cc_pass, spp * kCPS); abort(); }
+#else
+        (void)cc_pass;
+#endif
     }
-    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -937,7 +1072,12 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         if (len > 16) { ok = false; len = 16; }
         uint32_t line[32];
         memset(line, 0, sizeof line);
-        memcpy(line, &llr[llr_off[r]], (size_t)len * sizeof(double));
+        for (int e = 0; e < len; ++e) {   // lane e: low word of entry e, lane 16+e: high word (llr_of)
+            uint64_t bits;
+            memcpy(&bits, &llr[llr_off[r] + e], 8);
+            line[e] = (uint32_t)bits;
+            line[16 + e] = (uint32_t)(bits >> 32);
+        }
         stream.insert(stream.end(), line, line + 32);
     };
     // list R1 node: dense ranks of |llr| over all (element, symbol) of the node + the sign bits, 16 bits per entry
@@ -1055,8 +1195,8 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
             while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
         stream.insert(stream.end(), op_lines[i].begin(), op_lines[i].end());
     }
-    // pad to whole chunks of 4 lines and transpose each chunk to [lane][4]
-    while ((stream.size() / 32) % 4) stream.insert(stream.end(), 32, 0u);
+    // pad to whole ring stages (kCPS chunks of 4 lines) and transpose each chunk to [lane][4]
+    while ((stream.size() / 32) % (4 * kCPS)) stream.insert(stream.end(), 32, 0u);
     const int n_lines = (int)(stream.size() / 32);
     {
         std::vector<uint32_t> tr(stream.size());
@@ -1123,18 +1263,30 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         fprintf(stderr, "\n");
     }
     P.r1_words = has_r1 ? 7 * 32 * 3 : 0;
-    size_t words = (size_t)P.vwords * 32 + (size_t)P.xwords * 32 + (size_t)P.scrwords + kRingChunks * 128 + 128 + 32 + P.r1_words;
-    pl->smem = words * 4;
-    pl->ws_bytes_per_cta = (size_t)P.gwords * 32 * 4;
+    P.warp_words = (int)(((size_t)P.vwords * 32 + (size_t)P.xwords * 32 + (size_t)P.scrwords + 128 + 32 + P.r1_words + 3) & ~(size_t)3);
     pl->logL = logL;
     pl->ca = d.ca != 0;
     pl->fastk = max_special >= 0;
     const void *fn = fast_kernel_fn(logL, pl->ca, pl->fastk);
-    if (pl->smem > 200 * 1024) { free_fast_plan(pl); return; }
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess) { cudaGetLastError(); free_fast_plan(pl); return; }
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, pl->smem) != cudaSuccess || occ < 1) { cudaGetLastError(); free_fast_plan(pl); return; }
-    pl->ctas_per_sm = occ;
+    // CTA shape: as many consumer warps per CTA as keep the SM's warp slots full (the ring and the producer warp are
+    // shared by the CTA); POLAR_B200_WARPS_PER_CTA overrides (tuning knob)
+    const size_t ring_bytes = (size_t)kRingSlots * 512 + 2 * kStages * 8;
+    int best_w = 0, best_occ = 0;
+    const int want_w = getenv("POLAR_B200_WARPS_PER_CTA") ? atoi(getenv("POLAR_B200_WARPS_PER_CTA")) : 0;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); free_fast_plan(pl); return; }
+    for (int w = kMaxWarps; w >= 1; --w) {
+        if (want_w && w != std::min(want_w, kMaxWarps)) continue;
+        const size_t smem = (size_t)w * P.warp_words * 4 + ring_bytes;
+        if (smem > 200 * 1024) continue;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (w + 1) * 32, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (occ * w > best_occ * best_w) { best_w = w; best_occ = occ; }
+    }
+    if (best_w < 1 || best_occ < 1) { free_fast_plan(pl); return; }
+    P.warps = best_w;
+    pl->smem = (size_t)best_w * P.warp_words * 4 + ring_bytes;
+    pl->ws_bytes_per_cta = (size_t)P.gwords * 32 * 4 * best_w;
+    pl->ctas_per_sm = best_occ;
     pl->name = "scl_lut_warp";
     pl->ok = true;
 }
@@ -1142,7 +1294,8 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
 inline int fast_grid(const FastPlan &pl, long long B, int sm_count) {
     const int L = 1 << pl.logL, FPW = 32 / L;
     long long groups = (B + FPW - 1) / FPW;
-    return (int)std::max<long long>(1, std::min<long long>(groups, (long long)sm_count * pl.ctas_per_sm));
+    long long ctas = (groups + pl.p.warps - 1) / pl.p.warps;
+    return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sm_count * pl.ctas_per_sm));
 }
 
 inline int launch_fast_lut(const Dev &d, const FastPlan &pl, const void *d_in, int dtype, long long B, uint8_t *d_out,
@@ -1150,7 +1303,7 @@ inline int launch_fast_lut(const Dev &d, const FastPlan &pl, const void *d_in, i
     const int grid = fast_grid(pl, B, sm_count);
     void *args[] = {(void *)&d, (void *)&pl.p, (void *)&d_in, (void *)&dtype, (void *)&d_out, (void *)&B, (void *)&ws,
                     (void *)&d_err, (void *)&dbg_pm, (void *)&dbg_win};
-    cudaError_t e = cudaLaunchKernel(fast_kernel_fn(pl.logL, pl.ca, pl.fastk), dim3(grid), dim3(32), args, pl.smem, s);
+    cudaError_t e = cudaLaunchKernel(fast_kernel_fn(pl.logL, pl.ca, pl.fastk), dim3(grid), dim3((pl.p.warps + 1) * 32), args, pl.smem, s);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }

@@ -43,6 +43,12 @@ CASES = [
     ("fastscl", "FastSCLLUTDecoder", dict(N=512, K=256, L=8, B=16)),
     ("cafast", "CAFastSCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, B=8)),
     ("cafast_q", "CAFastSCLLUTDecoder", dict(N=256, K=152, A=128, L=4, B=24, Q=12, Qc=9)),
+    ("multi_pass", "SCLLUTDecoder", dict(N=128, K=64, L=8, B=1001)),
+    ("multi_pass_l1", "SCLUTDecoder", dict(N=64, K=30, B=3000)),
+    ("sclut_1024", "SCLUTDecoder", dict(N=1024, K=512, B=200, tables="minsum")),
+    ("cascl_1024", "CASCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, B=16, tables="minsum")),
+    ("cafast_1024m", "CAFastSCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, B=16, tables="minsum")),
+    ("fastsc_1024", "FastSCLUTDecoder", dict(N=1024, K=512, B=100, tables="minsum")),
     ("float_scl", "SCLDecoder", dict(N=128, K=64, L=8, B=16, tables="channel")),
     ("uniform_l32", "SCLUniformQuantizedDecoder", dict(N=128, K=64, L=32, B=8)),
 ]

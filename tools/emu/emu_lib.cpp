@@ -140,5 +140,7 @@ void pd_sim_destroy(pd_sim *) {}
 int pd_sim_generate(pd_sim *, double, int64_t, uint64_t, uint64_t, uint8_t *, void *, void *) { return PD_ECUDA; }
 int pd_sim_encode(pd_sim *, int, const uint8_t *, int64_t, uint8_t *) { return PD_ECUDA; }
 int pd_sim_encode_device(pd_sim *, int, const uint8_t *, int64_t, uint8_t *, void *) { return PD_ECUDA; }
+int pd_mmi_slice_sums(const double *, const double *, int32_t, int32_t, int32_t, double *, double *, int32_t) { return PD_ECUDA; }
+int pd_mmi_design(const double *, const double *, const double *, const double *, double, double, int32_t, int32_t, int32_t, int32_t *, int32_t) { return PD_ECUDA; }
 int pd_optls_quantize(const double *, const double *, const int32_t *, int64_t, int32_t, int32_t, double *, double *, int32_t *, int32_t) { return PD_ECUDA; }
 }
