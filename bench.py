@@ -1,13 +1,15 @@
 #!/usr/bin/env python
-"""Benchmark of the decode hot path on the north-star shape (BASELINE.json): SCL-LUT, N=1024, A=K=512, L=8,
-QDecoder=16, synthetic AWGN frames.
+"""Benchmark of the decode hot path.  Default: the north-star shape of BASELINE.json (SCL-LUT, N=1024, A=K=512, L=8,
+QDecoder=16); --config C1..C5 selects the other BASELINE.json configurations (synthetic AWGN frames of each shape).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NS|C1|C2|C3|C4|C5] [--batch F]
 
 A "step" decodes one batch of F frames per GPU (inputs > L2 so no flush is needed).  Prints ONE JSON line:
   value     decoded frames/s over all GPUs, inputs resident in HBM (pd_decode_device), CUDA-event timed, max over ranks
-  e2e       the same metric through the host-buffer C-ABI call pd_decode (pinned host in/out, H2D+D2H inside)
-  roofline  algorithmic bytes (N symbol bytes in + K bit bytes out per frame) / kernel time vs measured HBM peak
+  e2e       the same metric through the reference-facing call with HOST buffers, copies inside: the pybind class's
+            decode((B,N) numpy array of the dtype the reference drivers pass, pageable memory) -> C ABI pd_decode
+  e2e_pinned  pd_decode on caller-pinned uint8/fp64 buffers (what a C caller that owns its buffers gets)
+  roofline  algorithmic bytes (N symbols in + K bits out per frame) / kernel time vs measured HBM peak
   cpu_baseline  the compiled reference (oracle/_ref), one process per host core, on a bounded sample (N=1 only)
 `--impl reference` times the reference's own CPU implementation on the same workload instead.
 Multi-GPU: one process per GPU (torchrun); frames are sharded, no data-path collective; the only exchange is the
@@ -15,6 +17,7 @@ NCCL all-reduce of the two error counters (bit / block errors), inside the timed
 """
 import argparse
 import ctypes
+import importlib.util
 import json
 import os
 import subprocess
@@ -26,32 +29,89 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-
-N, K, L, Q = 1024, 512, 8, 16
-EBN0_DB = 2.0
-WORKLOAD = "SCL-LUT N=1024 A=K=512 L=8 QDecoder=QChannel=16, MinDistortion LUTs (reference generator, design 3 dB), AWGN Eb/N0=2.0 dB through the driver's channel quantizer, NR-sequence frozen set"
-METRIC = "decoded frames/s (info Gbit/s = frames/s*512/1e9), N=1024 L=8 SCL-LUT"
-BYTES_PER_FRAME = N + K  # uint8 symbols in + uint8 bits out
+PKG = os.path.join(ROOT, "quantized_decoder_polar_codes_b200")
 
 
-def make_workload(frames, seed):
-    """Real MinDistortion tables for N=1024, Q=16, design SNR 3 dB, produced by the reference's own generator code
-    (tests/golden/make_real_lut_n1024.py), the channel quantizer the reference driver builds at this Eb/N0
-    (mainQuantizedDecoder_LLRDomain.py:130-145) and its per-symbol rule (:167-176), vectorised."""
-    from quantized_decoder_polar_codes_b200 import simulation as sim
+def _sim():
+    """simulation.py (plain numpy helpers) loaded by path: the reference arm must not import the package, whose __init__
+    loads the CUDA extension"""
+    name = "_polar_b200_simulation"
+    if name not in sys.modules:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(PKG, "simulation.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+    return sys.modules[name]
+
+
+# BASELINE.json configurations.  api_dtype = what the reference driver of that configuration hands to decode().
+CONFIGS = {
+    "NS": dict(kind="SCLLUTDecoder", N=1024, A=512, K=512, L=8, ebn0=2.0, dev_dtype="u8", api_dtype="int32", frames=131072,
+               workload="SCL-LUT N=1024 A=K=512 L=8 QDecoder=QChannel=16, MinDistortion LUTs (reference generator, design 3 dB), AWGN Eb/N0=2.0 dB through the driver's channel quantizer, NR-sequence frozen set",
+               metric="decoded frames/s (info Gbit/s = frames/s*512/1e9), N=1024 L=8 SCL-LUT"),
+    "C1": dict(kind="SCDecoder", N=128, A=64, K=64, L=1, ebn0=2.0, dev_dtype="f64", api_dtype="float64", frames=1 << 19,
+               workload="float SC N=128 A=K=64, AWGN Eb/N0=2.0 dB channel LLRs (mainFPDecoder.py), NR-sequence frozen set",
+               metric="decoded frames/s, float SC N=128 A=64"),
+    "C2": dict(kind="SCLUTDecoder", N=128, A=32, K=32, L=1, ebn0=2.0, dev_dtype="u8", api_dtype="int32", frames=1 << 21,
+               workload="SC-LUT N=128 A=K=32 QDecoder=QChannel=16, MinDistortion LUTs (reference generator, design 3 dB), AWGN Eb/N0=2.0 dB",
+               metric="decoded frames/s, MinDistortion SC-LUT N=128 A=32"),
+    "C3": dict(kind="SCLLUTDecoder", N=128, A=32, K=32, L=8, ebn0=2.0, dev_dtype="u8", api_dtype="int32", frames=1 << 20,
+               workload="SCL-LUT N=128 A=K=32 L=8 QDecoder=QChannel=16, MinDistortion LUTs (reference generator, design 3 dB), AWGN Eb/N0=2.0 dB",
+               metric="decoded frames/s, MinDistortion SCL-LUT N=128 A=32 L=8"),
+    "C4": dict(kind="CAFastSCLLUTDecoder", N=1024, A=512, K=536, L=8, ebn0=2.0, dev_dtype="u8", api_dtype="float64", frames=131072,
+               workload="CRC-aided FastSCL-LUT N=1024 A=512 (+CRC-24, K=536) L=8 QDecoder=QChannel=16, MMI LUTs (probability domain, design 3 dB), AWGN Eb/N0=2.0 dB through the MMI channel quantizer",
+               metric="decoded frames/s, MMI CA-FastSCL-LUT N=1024 A=512 L=8"),
+    "C5": dict(kind="SCLUniformQuantizedDecoder", N=2048, A=1024, K=1024, L=32, ebn0=2.0, dev_dtype="f64", api_dtype="float64", frames=1 << 14,
+               workload="uniformly quantized SCL N=2048 A=K=1024 L=32 v=16, GA construction, optimal uniform step sizes (reference design code), AWGN Eb/N0=2.0 dB LLRs through QUniform",
+               metric="decoded frames/s, uniformly quantized SCL N=2048 A=1024 L=32"),
+}
+
+
+def make_workload(cfg, frames, seed):
+    """-> constructor kwargs (numpy tables), inputs [frames, N] in the device dtype, transmitted message [frames, A]"""
+    sim = _sim()
+    N, A, K, L, eb, kind = cfg["N"], cfg["A"], cfg["K"], cfg["L"], cfg["ebn0"], cfg["kind"]
     rng = np.random.default_rng(seed)
-    z = np.load(os.path.join(ROOT, "quantized_decoder_polar_codes_b200", "data", "mindistortion_n1024_q16_3dB.npz"))
+    if kind == "SCLUniformQuantizedDecoder":                 # C5 (mainQuantizedDecoder_ContinuousDomain.py:95-104,186-192)
+        v = 16
+        sigma = sim.awgn_sigma(eb, K / N)
+        fm, mm = sim.frozen_mask_ga(N, K, sigma)
+        r_f, r_g = sim.uniform_quantizer_steps(N, v, sigma)
+        msg = rng.integers(0, 2, (frames, K), dtype=np.uint8)
+        llr = sim.awgn_llr(sim.polar_encode(msg, fm), sigma, rng)
+        r = r_f[0]
+        M = (v // 2 - 0.5) * r
+        x = np.where(np.abs(llr) > M, np.sign(llr) * (M - 0.5 * r), (np.floor(llr / r) + 0.5) * r)
+        return dict(N=N, K=K, L=L, frozen_bits=fm, message_bits=mm, decoder_r_f=r_f, decoder_r_g=r_g, v=v), x, msg
     fm, mm = sim.frozen_mask(N, K)
-    f = [z["lut_f"][p].astype(np.int32)[None] for p in range(N - 1)]
-    g = [z["lut_g"][p].astype(np.int32)[None] for p in range(N - 1)]
-    llr_tab = z["llr_quanta"]
-    edges, clut = z[f"chan_A{K}_eb{EBN0_DB:.0f}/edges"], z[f"chan_A{K}_eb{EBN0_DB:.0f}/lut"]
-    msg = rng.integers(0, 2, (frames, K), dtype=np.uint8)
-    cw = sim.polar_encode(msg, fm)
-    llr = sim.awgn_llr(cw, sim.awgn_sigma(EBN0_DB, K / N), rng)
-    idx = np.clip(np.searchsorted(edges[:-1], llr, side="left") - 1, 0, clut.size - 1)
-    sym = np.where(llr <= edges[0], 0, np.where(llr >= edges[-1], Q - 1, clut[idx])).astype(np.uint8)
-    kw = dict(N=N, K=K, L=L, frozen_bits=fm, message_bits=mm, LUT_f=f, LUT_g=g, virtual_channel_llr=llr_tab)
+    msg = rng.integers(0, 2, (frames, A), dtype=np.uint8)
+    cw = sim.polar_encode(sim.crc_attach(msg) if K > A else msg, fm)
+    sigma = sim.awgn_sigma(eb, A / N)
+    kw = dict(N=N, K=K, frozen_bits=fm, message_bits=mm)
+    if kind == "SCDecoder":                                  # C1
+        return kw, sim.awgn_llr(cw, sigma, rng), msg
+    if L > 1:
+        kw["L"] = L
+    if kind == "CAFastSCLLUTDecoder":                        # C4: MMI tables, symbols cut from y (probability-domain driver)
+        z = np.load(os.path.join(PKG, "data", "mmi_n1024_q16_3dB.npz"))
+        kw.update(A=A, node_type=sim.identify_nodes(N, fm), virtual_channel_llr=z["llrs"])
+        edges = z[f"chan_A{A}_eb{eb:.0f}/edges"]
+        y = (1.0 - 2.0 * cw) + rng.normal(0.0, sigma, cw.shape)
+        sym = np.where(y <= edges[0], 0, np.where(y >= edges[-1], 15, np.searchsorted(edges, y, side="left") - 1)).astype(np.uint8)
+    else:                                                    # NS / C2 / C3: MinDistortion tables, LLR-domain driver's quantizer
+        if N == 1024:
+            z = np.load(os.path.join(PKG, "data", "mindistortion_n1024_q16_3dB.npz"))
+            edges, clut = z[f"chan_A{A}_eb{eb:.0f}/edges"], z[f"chan_A{A}_eb{eb:.0f}/lut"]
+            kw["virtual_channel_llr"] = z["llr_quanta"]
+        else:
+            z = np.load(os.path.join(ROOT, "tests", "golden", "real_lut_n128.npz"))
+            edges, clut = z[f"A{A}_eb{eb:.0f}/chan_edges"], z[f"A{A}_eb{eb:.0f}/chan_lut"]
+            kw["virtual_channel_llr"] = z["llr_quanta"]
+        llr = sim.awgn_llr(cw, sigma, rng)
+        idx = np.clip(np.searchsorted(edges[:-1], llr, side="left") - 1, 0, clut.size - 1)
+        sym = np.where(llr <= edges[0], 0, np.where(llr >= edges[-1], 15, clut[idx])).astype(np.uint8)
+    kw["LUT_f"] = [z["lut_f"][p].astype(np.int32)[None] for p in range(N - 1)]
+    kw["LUT_g"] = [z["lut_g"][p].astype(np.int32)[None] for p in range(N - 1)]
     return kw, sym, msg
 
 
@@ -132,34 +192,48 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
+def _ref_kwargs(kw):
+    """numpy tables -> the nested lists the compiled reference takes, one table per position (tests/common.py: ref_kwargs)"""
+    out, N = {}, kw["N"]
+    for k, val in kw.items():
+        if k in ("LUT_f", "LUT_g"):
+            lst = []
+            for p_, t in enumerate(val):
+                t = np.asarray(t)
+                npos = N >> (int(np.floor(np.log2(p_ + 1))) + 1)
+                lst.append((np.broadcast_to(t, (npos,) + t.shape[1:]) if t.shape[0] == 1 and npos > 1 else t).tolist())
+            out[k] = lst
+        else:
+            out[k] = val.tolist() if isinstance(val, np.ndarray) else val
+    return out
+
+
 def _ref_worker(args):
-    kw_small, sym, core = args
+    kind, kw, x, core = args
     try:
         os.sched_setaffinity(0, {core})
     except Exception:
         pass
     sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import polar_oracle as po
-    import common
     ref = po.load_reference()
-    t0 = time.perf_counter()
+    lut = "LUT" in kind
+    xx = x.astype(np.int32) if lut else x.astype(np.float64)
     if ref is not None:
-        dec = ref.SCLLUTDecoder(**common.ref_kwargs(kw_small))
-        x = sym.astype(np.int32)
+        dec = getattr(ref, kind)(**_ref_kwargs(kw))
         t0 = time.perf_counter()
-        for i in range(x.shape[0]):
-            dec.decode(x[i])
-        kind = "reference"
+        for i in range(xx.shape[0]):
+            dec.decode(xx[i])
+        how = "reference"
     else:
-        dec = po.OracleDecoder("SCLLUTDecoder", **kw_small)
+        dec = po.OracleDecoder(kind, **kw)
         t0 = time.perf_counter()
-        dec.decode(sym.astype(np.int32))
-        kind = "port"
-    return time.perf_counter() - t0, kind
+        dec.decode(xx)
+        how = "port"
+    return time.perf_counter() - t0, how
 
 
-def cpu_reference_throughput(kw, sym, frames_per_core, cores=None):
+def cpu_reference_throughput(kind, kw, x, frames_per_core, cores=None):
     """The reference's own CPU decode() (oracle/_ref) on `cores` pinned processes, disjoint shards of the same
     pre-generated inputs; frames/s = total frames / slowest process wall time."""
     import multiprocessing as mp
@@ -167,10 +241,10 @@ def cpu_reference_throughput(kw, sym, frames_per_core, cores=None):
     cores = cores or len(avail)
     jobs = []
     for c in range(cores):
-        shard = sym[(c * frames_per_core) % sym.shape[0]:][:frames_per_core]
+        shard = x[(c * frames_per_core) % x.shape[0]:][:frames_per_core]
         if shard.shape[0] < frames_per_core:
-            shard = np.tile(sym, (-(-frames_per_core // sym.shape[0]), 1))[:frames_per_core]
-        jobs.append((kw, shard, avail[c % len(avail)]))
+            shard = np.tile(x, (-(-frames_per_core // x.shape[0]), 1))[:frames_per_core]
+        jobs.append((kind, kw, shard, avail[c % len(avail)]))
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         res = pool.map(_ref_worker, jobs)
@@ -178,25 +252,34 @@ def cpu_reference_throughput(kw, sym, frames_per_core, cores=None):
     return cores * frames_per_core / wall, cores, res[0][1], wall
 
 
+def ref_frames_per_core(cfg, args):
+    """bounded sample: a few seconds of CPU work per step and core (the reference needs 20 ms per N=1024 L=8 frame, 2 s per C5 frame)"""
+    if args.ref_frames > 0:
+        return args.ref_frames
+    return {"NS": 400, "C4": 400, "C1": 200000, "C2": 100000, "C3": 20000, "C5": 4}[args.config]
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    kw, sym, _ = make_workload(256, seed=0)
-    fpc = args.ref_frames
+    cfg = CONFIGS[args.config]
+    fpc = ref_frames_per_core(cfg, args)
+    kw, x, _ = make_workload(cfg, min(256 if cfg["N"] >= 1024 else 4096, max(fpc, 16)), seed=0)
     times = []
     for it in range(args.warmup + args.steps):
-        fps, cores, kind, wall = cpu_reference_throughput(kw, sym, fpc)
+        fps, cores, how, wall = cpu_reference_throughput(cfg["kind"], kw, x, fpc)
         if it >= args.warmup:
             times.append((fps, wall))
     fps = float(np.mean([t[0] for t in times]))
     ms = float(np.mean([t[1] for t in times]) * 1e3)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": cores * fpc, "info_gbit_s": fps * K / 1e9},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+        "dtype": cfg["dev_dtype"], "data": "synthetic",
+        "config": {"workload": cfg["workload"], "name": args.config},
+        "run": {"frames_per_step": cores * fpc, "info_gbit_s": fps * cfg["A"] / 1e9},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": how,
                          "sample": f"{fpc} frames per core per step, one pinned process per core, per-frame decode() calls"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -211,47 +294,60 @@ def run_ours(args, rank, local_rank, world):
     from quantized_decoder_polar_codes_b200 import capi
     from quantized_decoder_polar_codes_b200 import distributed as D
 
+    cfg = CONFIGS[args.config]
+    N, A, kind = cfg["N"], cfg["A"], cfg["kind"]
+    lut = cfg["dev_dtype"] == "u8"
+    esz = 1 if lut else 8
+    pd_dtype = capi.PD_U8 if lut else capi.PD_F64
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     D.init("nccl", dev)
-    kw, sym0, msg0 = make_workload(8192, seed=rank)
-    dec = q.SCLLUTDecoder(device=local_rank, **kw)
+    kw, x0, msg0 = make_workload(cfg, 8192 if N >= 1024 else 65536, seed=rank)
+    dec = getattr(q, kind)(device=local_rank, **kw)
     lib = capi.lib()
+    Kout = lib.pd_out_len(dec._handle)
+    bytes_per_frame = N * esz + Kout               # symbols (or fp64 LLRs) in + one byte per decoded bit out
     # frames per step: --batch, or by default the multiple of the kernel's wave (SMs x resident warps x frames per warp)
-    # nearest to 131072 -- a persistent kernel then has no tail
+    # nearest to the configuration's nominal batch
     F = args.batch
-    wave = capi.wave_frames(dec, capi.PD_U8)
+    wave = capi.wave_frames(dec, pd_dtype)
     if F <= 0:
-        F = max(1, round(131072 / wave)) * wave if wave > 0 else 131072
-    sym, msg = tile_frames(sym0, msg0, F)
+        F = max(1, round(cfg["frames"] / wave)) * wave if wave > 0 else cfg["frames"]
+    x, msg = tile_frames(x0, msg0, F)
     stream = torch.cuda.current_stream().cuda_stream
 
-    d_in = torch.from_numpy(sym).to(dev)
+    d_in = torch.from_numpy(x).to(dev)
     d_truth = torch.from_numpy(msg).to(dev)
-    d_out = torch.empty((F, K), dtype=torch.uint8, device=dev)
+    d_out = torch.empty((F, Kout), dtype=torch.uint8, device=dev)
     counters = torch.zeros(2, dtype=torch.int64, device=dev)   # run totals (identical on every rank)
     step_cnt = torch.zeros(2, dtype=torch.int64, device=dev)   # this step's local counts -> all-reduced -> added to the totals
-    assert d_in.numel() >= 120 * 2 ** 20 or 0 < args.batch < 131072, "inputs + outputs of a step must exceed L2"
+    l2_note = "inputs+outputs per step exceed L2 (no flush needed)" if F * bytes_per_frame > 126 * 2 ** 20 else "batch below L2 size"
+    assert Kout == A, "the error counters compare A message bits"
 
     def count_and_reduce():
         step_cnt.zero_()
-        capi.check(lib.pd_count_errors(d_out.data_ptr(), d_truth.data_ptr(), F, K, step_cnt.data_ptr(), stream))
+        capi.check(lib.pd_count_errors(d_out.data_ptr(), d_truth.data_ptr(), F, A, step_cnt.data_ptr(), stream))
         D.allreduce_counters(step_cnt)   # the path's only exchange: 2 x int64 over NCCL/NVLink
         counters.add_(step_cnt)
 
     def step_device():
-        capi.decode_device(dec, d_in.data_ptr(), capi.PD_U8, F, d_out.data_ptr(), stream)
+        capi.decode_device(dec, d_in.data_ptr(), pd_dtype, F, d_out.data_ptr(), stream)
         count_and_reduce()
 
     def barrier():
         D.barrier()
         torch.cuda.synchronize()
 
-    launches0 = lib.pd_launch_count()
+    def note(msg):
+        if args.verbose and rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    note(f"workload ready: F={F} wave={wave} kernel={dec.kernel}")
     for _ in range(args.warmup):
         counters.zero_()
         step_device()
     barrier()
+    note("warm-up done")
     # --- device-resident timing: whole step and the decode kernel alone (roofline) ---
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -262,7 +358,7 @@ def run_ours(args, rank, local_rank, world):
         ev[0].record()
         for i in range(args.steps):
             kev[i][0].record()
-            capi.decode_device(dec, d_in.data_ptr(), capi.PD_U8, F, d_out.data_ptr(), stream)
+            capi.decode_device(dec, d_in.data_ptr(), pd_dtype, F, d_out.data_ptr(), stream)
             kev[i][1].record()
             count_and_reduce()
         ev[1].record()
@@ -276,23 +372,41 @@ def run_ours(args, rank, local_rank, world):
     value = world * F * args.steps / (elapsed_ms / 1e3)
     cnt = counters.cpu().tolist()
     total_frames = world * F * args.steps
+    ref_out = d_out.cpu().numpy()
+    note(f"device-resident: {value:.4g} frames/s")
 
-    # --- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside) ---
-    h_in_p = lib.pd_host_alloc(F * N)
-    h_out_p = lib.pd_host_alloc(F * K)
-    h_in = np.ctypeslib.as_array(ctypes.cast(h_in_p, ctypes.POINTER(ctypes.c_uint8)), (F, N))
-    h_out = np.ctypeslib.as_array(ctypes.cast(h_out_p, ctypes.POINTER(ctypes.c_uint8)), (F, K))
-    h_in[:] = sym
-    for _ in range(max(1, args.warmup // 2)):
-        capi.decode_host(dec, h_in_p, capi.PD_U8, F, h_out_p)
+    # --- end to end (1): the reference-facing call.  decode((B,N) array) of the pybind class, input in the dtype and kind of
+    #     memory the reference drivers use (pageable numpy: int32 symbols / float64), result a fresh numpy array ---
+    x_api = x.astype(cfg["api_dtype"])
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(2):
+        got = dec.decode(x_api)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        capi.decode_host(dec, h_in_p, capi.PD_U8, F, h_out_p)
+    for _ in range(e2e_steps):
+        got = dec.decode(x_api)
+    e2e_api_s = time.perf_counter() - t0
+    e2e_value = world * F * e2e_steps / D.max_over_ranks(e2e_api_s, dev)
+    same_api = bool((got == ref_out).all())
+    del x_api
+    note(f"e2e through decode(): {e2e_value:.4g} frames/s")
+
+    # --- end to end (2): the C ABI's host-buffer call on caller-pinned buffers in the compact device dtype ---
+    h_in_p = lib.pd_host_alloc(F * N * esz)
+    h_out_p = lib.pd_host_alloc(F * Kout)
+    h_in = np.ctypeslib.as_array(ctypes.cast(h_in_p, ctypes.POINTER(ctypes.c_uint8 if lut else ctypes.c_double)), (F, N))
+    h_out = np.ctypeslib.as_array(ctypes.cast(h_out_p, ctypes.POINTER(ctypes.c_uint8)), (F, Kout))
+    h_in[:] = x
+    for _ in range(2):
+        capi.decode_host(dec, h_in_p, pd_dtype, F, h_out_p)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        capi.decode_host(dec, h_in_p, pd_dtype, F, h_out_p)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_value = world * F * args.steps / D.max_over_ranks(e2e_s, dev)
-    same = bool((h_out == d_out.cpu().numpy()).all())
+    e2e_pinned = world * F * e2e_steps / D.max_over_ranks(e2e_s, dev)
+    same = bool((h_out == ref_out).all())
     lib.pd_host_free(h_in_p)
     lib.pd_host_free(h_out_p)
 
@@ -303,36 +417,40 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = BYTES_PER_FRAME * F / (kernel_ms / 1e3) / 1e9
+        achieved = bytes_per_frame * F / (kernel_ms / 1e3) / 1e9
         traffic = None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel, per frame
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if tj.get("kernel") == dec.kernel:
+            if tj.get("kernel") == dec.kernel and tj.get("config", "NS") == args.config:
                 traffic = tj["dram_bytes_per_frame"] * F
         except Exception:
             pass
+        n_launch = int(l_after - l_before)
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": cfg["metric"], "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "wave_frames": wave, "info_gbit_s": value * K / 1e9, "kernel": dec.kernel,
-                       "l2": "inputs+outputs per step exceed L2 (no flush needed)" if F * BYTES_PER_FRAME > 126 * 2 ** 20 else "batch below L2 size",
-                       "bit_errors": cnt[0], "block_errors": cnt[1], "frames_counted": total_frames,
-                       "e2e_equals_device_output": same},
+            "dtype": cfg["dev_dtype"], "data": "synthetic",
+            "config": {"workload": cfg["workload"], "name": args.config},
+            "run": {"frames_per_step_per_gpu": F, "wave_frames": wave, "info_gbit_s": value * A / 1e9, "kernel": dec.kernel, "l2": l2_note,
+                    "bit_errors": cnt[0], "block_errors": cnt[1], "frames_counted": total_frames,
+                    "unique_frames": int(x0.shape[0]), "e2e_outputs_equal_device_output": same and same_api},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "kernel_ms": kernel_ms, "bytes_per_frame": BYTES_PER_FRAME,
-                         "per": "decode call of one step = 4 scl_lut_warp launches overlapped on two internal streams; algorithmic bytes, kernel_ms and traffic all refer to that call",
+                         "kernel_ms": kernel_ms, "bytes_per_frame": bytes_per_frame,
+                         "per": f"decode call of one step ({(n_launch // args.steps) - 1} {dec.kernel} launches); algorithmic bytes, kernel_ms and traffic all refer to that call",
                          "note": "HBM-nominal codec path; the kernel is SM-issue bound, not HBM bound (see DESIGN.md 4.1, profiles/)"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * N, "d2h_bytes_per_step": F * K},
-            "gpu_launches": int(l_after - l_before),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * N * esz, "d2h_bytes_per_step": F * Kout,
+                    "call": f"{kind}.decode(({F},{N}) {cfg['api_dtype']} numpy array, pageable) -> pd_decode; {F * N * np.dtype(cfg['api_dtype']).itemsize} host bytes read per step"},
+            "e2e_pinned": {"value": e2e_pinned, "unit": "frames/s", "call": "pd_decode on pd_host_alloc'ed buffers in the device dtype"},
+            "gpu_launches": n_launch,
             "clocks": clk.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                fps, cores, kind, wall = cpu_reference_throughput(kw, sym0[:256], args.ref_frames)
-                line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                                        "sample": f"{args.ref_frames} frames per core ({wall:.1f} s), one pinned process per core, per-frame decode() calls of the compiled reference"}
+                fpc = ref_frames_per_core(cfg, args)
+                fps, cores, how, wall = cpu_reference_throughput(kind, kw, x0[:256 if N >= 1024 else 4096], fpc)
+                line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": how,
+                                        "sample": f"{fpc} frames per core ({wall:.1f} s), one pinned process per core, per-frame decode() calls of the compiled reference"}
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
         emit(json.dumps(line))
@@ -366,9 +484,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (default: the whole number of kernel waves nearest to 131072)")
-    ap.add_argument("--ref-frames", type=int, default=400, help="CPU reference: frames per core per step")
+    ap.add_argument("--config", default="NS", choices=sorted(CONFIGS), help="BASELINE.json configuration (NS = the north-star shape)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (default: the whole number of kernel waves nearest to the configuration's nominal batch)")
+    ap.add_argument("--ref-frames", type=int, default=0, help="CPU reference: frames per core per step (default: a few seconds of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="progress notes on stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -378,6 +498,9 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     protect_stdout()
+    if args.verbose:
+        import faulthandler
+        faulthandler.dump_traceback_later(90, repeat=True, file=sys.stderr)   # where it hangs, if it hangs
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -118,6 +118,16 @@ int64_t pd_wave_frames(const pd_decoder *dec, int in_dtype);
  * threads at once. */
 int pd_decode(pd_decoder *dec, const void *host_in, int in_dtype, int64_t B, uint8_t *host_out);
 
+/* In-library multi-GPU: after pd_set_devices(dec, n, ids) every pd_decode call deals its batch, chunk by chunk,
+ * to the n CUDA devices `ids` of the box -- the tables and the compiled schedule are cloned onto each of them, frames are
+ * independent, so there is no data-path exchange at all.  n = 0 goes back to the decoder's own device.  An id may repeat
+ * (two pipelines on one GPU).  pd_decode_device / pd_check / pd_wave_frames keep referring to the decoder's own device.
+ * pd_counters_allreduce sums the per-device {bit errors, block errors} pairs of pd_count_errors over the decoder's devices and
+ * writes the total back to each (dev_counters[i] lives on device i of the list). */
+int pd_set_devices(pd_decoder *dec, int32_t n, const int32_t *device_ids);
+int32_t pd_device_count(const pd_decoder *dec);
+int pd_counters_allreduce(pd_decoder *dec, unsigned long long *const *dev_counters, int32_t n);
+
 /* Same with device-resident buffers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).
  * Input symbol range errors are reported by the next pd_check(). */
 int pd_decode_device(pd_decoder *dec, const void *dev_in, int in_dtype, int64_t B, uint8_t *dev_out,

@@ -12,9 +12,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <limits>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/polar_b200.h"
 #include "pb_internal.h"
@@ -115,9 +122,132 @@ struct StreamSlot {
     uint8_t *d_out = nullptr;
     char *ws = nullptr;
     size_t in_cap = 0, out_cap = 0, ws_cap = 0;
+    // pd_decode with pageable / int32 host buffers: pinned staging areas and the event that says the chunk's result is in h_out
+    char *h_in = nullptr, *h_out = nullptr;
+    size_t h_in_cap = 0, h_out_cap = 0;
+    cudaEvent_t done = nullptr;
 };
 
 }  // namespace
+
+// ---- host-side staging of pd_decode ------------------------------------------------------------------------------
+// A small persistent pool: pd_decode converts / copies the caller's (pageable, possibly int32) buffers to and from pinned
+// staging memory with all host cores while the previous chunk is on the GPU.
+namespace {
+class HostPool {
+public:
+    static HostPool &get() { static HostPool p; return p; }
+    int size() const { return (int)workers_.size() + 1; }
+    // runs fn(part) for part = 0 .. parts-1 on the pool (the caller takes part too) and waits
+    void run(int parts, const std::function<void(int)> &fn) {
+        if (parts <= 1 || workers_.empty()) { for (int i = 0; i < parts; ++i) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn; parts_ = parts; next_ = 0; done_ = 0; ++gen_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return done_ == parts_; });
+        fn_ = nullptr;
+    }
+private:
+    HostPool() {
+        int n = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("POLAR_B200_HOST_THREADS")) n = atoi(e);
+        n = std::max(1, std::min(n, 32));
+        for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void work() {
+        for (;;) {
+            int i;
+            { std::lock_guard<std::mutex> lk(m_); if (!fn_ || next_ >= parts_) return; i = next_++; }
+            (*fn_)(i);
+            { std::lock_guard<std::mutex> lk(m_); if (++done_ == parts_) cv_done_.notify_all(); }
+        }
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> lk(m_); cv_.wait(lk, [&] { return gen_ != seen; }); seen = gen_; if (stop_) return; }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int parts_ = 0, next_ = 0, done_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+
+// n int32 symbols -> bytes; returns false if a value does not fit a byte (the kernels then never see it)
+bool narrow_i32_to_u8(const int32_t *src, uint8_t *dst, size_t n) {
+    uint32_t bad = 0;
+    size_t i = 0;
+#if defined(__SSE2__)
+    const bool nt = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    __m128i acc = _mm_setzero_si128();
+    for (; i + 16 <= n; i += 16) {
+        const __m128i a0 = _mm_loadu_si128((const __m128i *)(src + i)), a1 = _mm_loadu_si128((const __m128i *)(src + i + 4));
+        const __m128i a2 = _mm_loadu_si128((const __m128i *)(src + i + 8)), a3 = _mm_loadu_si128((const __m128i *)(src + i + 12));
+        acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(a0, a1), _mm_or_si128(a2, a3)));
+        const __m128i r = _mm_packus_epi16(_mm_packs_epi32(a0, a1), _mm_packs_epi32(a2, a3));
+        if (nt) _mm_stream_si128((__m128i *)(dst + i), r);     // pinned staging area: written once, read by the copy engine
+        else _mm_storeu_si128((__m128i *)(dst + i), r);
+    }
+    if (nt) _mm_sfence();
+    alignas(16) uint32_t lanes[4];
+    _mm_store_si128((__m128i *)lanes, acc);
+    bad = lanes[0] | lanes[1] | lanes[2] | lanes[3];
+#endif
+    for (; i < n; ++i) { bad |= (uint32_t)src[i]; dst[i] = (uint8_t)src[i]; }
+    return (bad & 0xffffff00u) == 0;
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+// Deep copy of the constructor arguments: pd_set_devices clones the decoder onto other GPUs from it.
+struct ConfigCopy {
+    pd_config c{};
+    std::vector<int32_t> frozen, node_type, crc_loc, lut_pool, f_npos, g_npos, f_qa, f_qb, g_qa, g_qb;
+    std::vector<int64_t> f_off, g_off, llr_off;
+    std::vector<double> llr_pool, r_f, r_g, bf, bg, rf, rg;
+    void take(const pd_config *src) {
+        c = *src;
+        const size_t N = (size_t)src->N;
+        auto cp = [](auto &vec, const auto *ptr, size_t n, const auto *&field) {
+            if (ptr && n) { vec.assign(ptr, ptr + n); field = vec.data(); } else { vec.clear(); field = nullptr; }
+        };
+        cp(frozen, src->frozen_bits, N, c.frozen_bits);
+        cp(node_type, src->node_type, 2 * N - 1, c.node_type);
+        cp(crc_loc, src->crc_loc, (size_t)std::max(0, src->crc_loc_len), c.crc_loc);
+        cp(lut_pool, src->lut_pool, (size_t)std::max<int64_t>(0, src->lut_pool_len), c.lut_pool);
+        cp(f_off, src->f_off, N - 1, c.f_off); cp(g_off, src->g_off, N - 1, c.g_off);
+        cp(f_npos, src->f_npos, N - 1, c.f_npos); cp(g_npos, src->g_npos, N - 1, c.g_npos);
+        cp(f_qa, src->f_qa, N - 1, c.f_qa); cp(f_qb, src->f_qb, N - 1, c.f_qb);
+        cp(g_qa, src->g_qa, N - 1, c.g_qa); cp(g_qb, src->g_qb, N - 1, c.g_qb);
+        const size_t rows = src->llr_off ? (size_t)src->llr_levels * N : 0;
+        cp(llr_off, src->llr_off, rows ? rows + 1 : 0, c.llr_off);
+        cp(llr_pool, src->llr_pool, rows ? (size_t)src->llr_off[rows] : 0, c.llr_pool);
+        cp(r_f, src->decoder_r_f, N - 1, c.decoder_r_f); cp(r_g, src->decoder_r_g, N - 1, c.decoder_r_g);
+        cp(bf, src->boundaries_f, (N - 1) * (size_t)std::max(0, src->n_boundaries), c.boundaries_f);
+        cp(bg, src->boundaries_g, (N - 1) * (size_t)std::max(0, src->n_boundaries), c.boundaries_g);
+        cp(rf, src->reconstruction_f, (N - 1) * (size_t)std::max(0, src->n_reconstruction), c.reconstruction_f);
+        cp(rg, src->reconstruction_g, (N - 1) * (size_t)std::max(0, src->n_reconstruction), c.reconstruction_g);
+    }
+};
 
 struct pd_decoder {
     Dev dev{};
@@ -150,6 +280,11 @@ struct pd_decoder {
     // pd_decode, tiny calls (the reference drivers decode one frame per call): a mapped pinned staging area the kernel
     // reads and writes directly -- no copy engine round trips
     char *h_small = nullptr, *d_small = nullptr;
+    // pd_set_devices: the batch of a pd_decode call is dealt chunk by chunk to `units` (this decoder and its clones on other
+    // GPUs of the box); empty = this decoder alone
+    ConfigCopy cfg;
+    std::vector<pd_decoder *> clones;     // owned
+    std::vector<pd_decoder *> units;      // not owned: this and / or clones, in the order of the device list
 };
 constexpr size_t kSmallIn = 64 << 10, kSmallOut = 16 << 10;   // bytes of input / output served by the mapped path
 
@@ -321,7 +456,7 @@ int plan_generic(pd_decoder *D) {
     const Dev &d = D->dev;
     int L = d.list ? d.L : 1;
     size_t vsz = d.domain == DOM_LUT ? 1 : 8;
-    size_t ws = (size_t)L * d.N * vsz + (size_t)L * d.r1_tmax * (8 + 4) + (size_t)L * 3 * d.N + (size_t)2 * L * d.r1_tmax + d.N;
+    size_t ws = (((size_t)L * d.N * vsz + 15) & ~(size_t)15) + (size_t)L * d.r1_tmax * (8 + 4) + (size_t)L * 3 * d.N + (size_t)2 * L * d.r1_tmax + d.N;
     ws = (ws + 15) & ~(size_t)15;
     D->ws_bytes = ws;
     int64_t work = (int64_t)L * d.N / 2;
@@ -330,7 +465,9 @@ int plan_generic(pd_decoder *D) {
     D->threads = th;
     D->use_smem = ws <= 96 * 1024;
     const void *fn = generic_fn_for(D);
-    if (D->use_smem) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+    // (the attribute belongs to the kernel function, which every decoder of the same domain shares: always the cap, never
+    //  this decoder's own size -- a smaller decoder created later must not shrink it under a live larger one)
+    if (D->use_smem) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, th, D->use_smem ? ws : 0));
     if (occ < 1) return fail(PD_ECUDA, "generic kernel does not fit on the device (ws=%zu)", ws);
@@ -398,10 +535,15 @@ int64_t pd_launch_count(void) { return g_launches.load(); }
 
 void pd_destroy(pd_decoder *D) {
     if (!D) return;
+    for (pd_decoder *c : D->clones) pd_destroy(c);
+    D->clones.clear();
     cudaSetDevice(D->device);
     for (auto &sl : D->slot) {
         if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
         cudaFree(sl.d_in); cudaFree(sl.d_out); cudaFree(sl.ws);
+        if (sl.h_in) cudaFreeHost(sl.h_in);
+        if (sl.h_out) cudaFreeHost(sl.h_out);
+        if (sl.done) cudaEventDestroy(sl.done);
     }
     cudaFree(D->ws_user);
     if (D->h_err) cudaFreeHost((void *)D->h_err);
@@ -494,12 +636,31 @@ int pd_create(const pd_config *c, pd_decoder **out) {
     } else if (d.domain == DOM_UNIFORM) {
         if (!c->decoder_r_f || !c->decoder_r_g) return bail(fail(PD_EINVAL, "decoder_r_f / decoder_r_g missing"));
         std::vector<double> rf(c->decoder_r_f, c->decoder_r_f + N - 1), rg(c->decoder_r_g, c->decoder_r_g + N - 1);
+        for (int i = 0; i < N - 1; ++i)
+            if (!(rf[i] > 0) || !(rg[i] > 0) || !std::isfinite(rf[i]) || !std::isfinite(rg[i]))
+                return bail(fail(PD_EINVAL, "decoder_r_f / decoder_r_g[%d] must be finite and > 0", i));
+        if (c->v < 2) return bail(fail(PD_EINVAL, "v=%d must be >= 2", c->v));
         if ((rc = upload(D, rf, &d.r_f)) || (rc = upload(D, rg, &d.r_g))) return bail(rc);
         d.mf_mul = double(c->v / 2 - 0.5);
         d.mg_mul = double(c->v / 2 - 1);
     } else if (d.domain == DOM_LLOYD) {
         if (!c->boundaries_f || !c->boundaries_g || !c->reconstruction_f || !c->reconstruction_g) return bail(fail(PD_EINVAL, "Lloyd tables missing"));
         if (c->n_boundaries < 1 || c->n_reconstruction < 1) return bail(fail(PD_EINVAL, "Lloyd table widths missing"));
+        // bisect() returns reconstruction[lo-1] with lo in [0, n_boundaries] (PD/src/utils.cpp:12-24): the reference reads
+        // out of bounds unless the first boundary is below every input and there is a cell per boundary gap
+        if (c->n_reconstruction < c->n_boundaries - 1) return bail(fail(PD_EINVAL, "Lloyd tables: %d reconstruction values for %d boundaries (need >= boundaries-1)", c->n_reconstruction, c->n_boundaries));
+        for (int t = 0; t < 2; ++t) {
+            const double *bd = t ? c->boundaries_g : c->boundaries_f;
+            for (int p = 0; p < N - 1; ++p) {
+                const double *row = bd + (size_t)p * c->n_boundaries;
+                for (int k = 0; k < c->n_boundaries; ++k) {
+                    if (row[k] != row[k]) return bail(fail(PD_EINVAL, "boundaries_%s[%d][%d] is NaN", t ? "g" : "f", p, k));
+                    if (k && row[k] < row[k - 1]) return bail(fail(PD_EINVAL, "boundaries_%s[%d] must ascend", t ? "g" : "f", p));
+                }
+                if (!(row[0] <= -1e290)) return bail(fail(PD_EINVAL, "boundaries_%s[%d][0] must be the -1e300 sentinel of LloydQuantizer.py:64 (a value below it reads reconstruction[-1] in the reference)", t ? "g" : "f", p));
+                if (c->n_reconstruction < c->n_boundaries && !(row[c->n_boundaries - 1] >= 1e290)) return bail(fail(PD_EINVAL, "boundaries_%s[%d]: last boundary must be the +1e300 sentinel when there are fewer reconstruction values than boundaries", t ? "g" : "f", p));
+            }
+        }
         size_t nbs = (size_t)(N - 1) * c->n_boundaries, nrs = (size_t)(N - 1) * c->n_reconstruction;
         std::vector<double> bf(c->boundaries_f, c->boundaries_f + nbs), bg(c->boundaries_g, c->boundaries_g + nbs);
         std::vector<double> rf(c->reconstruction_f, c->reconstruction_f + nrs), rg(c->reconstruction_g, c->reconstruction_g + nrs);
@@ -521,7 +682,58 @@ int pd_create(const pd_config *c, pd_decoder **out) {
     D->kernel_name = (D->fast.ok && D->force == 0) ? D->fast.name : (D->path.ok && D->force != 1) ? "path_warp" : "generic";
     size_t in_frame = (size_t)N * (d.domain == DOM_LUT ? 4 : 8);
     D->chunk_frames = std::max<int64_t>(1024, (int64_t)((32u << 20) / in_frame));
+    D->cfg.take(c);
     *out = D;
+    return PD_OK;
+}
+
+int pd_set_devices(pd_decoder *D, int32_t n, const int32_t *ids) {
+    if (!D || n < 0 || (n > 0 && !ids)) return fail(PD_EINVAL, "null argument");
+    for (pd_decoder *c : D->clones) pd_destroy(c);
+    D->clones.clear();
+    D->units.clear();
+    if (n == 0) return PD_OK;
+    if (n > 64) return fail(PD_EINVAL, "at most 64 devices");
+    bool self_used = false;
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] == D->device && !self_used) { D->units.push_back(D); self_used = true; continue; }
+        pd_config c = D->cfg.c;
+        c.device = ids[i];
+        pd_decoder *clone = nullptr;
+        const int rc = pd_create(&c, &clone);
+        if (rc != PD_OK) {
+            for (pd_decoder *q : D->clones) pd_destroy(q);
+            D->clones.clear();
+            D->units.clear();
+            return rc;
+        }
+        clone->force = D->force;
+        D->clones.push_back(clone);
+        D->units.push_back(clone);
+    }
+    CUDA_TRY(cudaSetDevice(D->device));
+    return PD_OK;
+}
+int32_t pd_device_count(const pd_decoder *D) { return D ? (int32_t)std::max<size_t>(1, D->units.size()) : 0; }
+
+int pd_counters_allreduce(pd_decoder *D, unsigned long long *const *dev_counters, int32_t n) {
+    // sums the n per-device counter pairs {bit errors, block errors} (pd_count_errors) and writes the total back to each of
+    // them.  One process drives all GPUs here, so 16 bytes per device travel through the host; the one-process-per-GPU
+    // front-end (bench.py, simulate.py under torchrun) all-reduces the same two words with NCCL over NVLink instead.
+    if (!D || !dev_counters || n < 1 || n != pd_device_count(D)) return fail(PD_EINVAL, "need one counter buffer per device of the decoder");
+    unsigned long long tot[2] = {0, 0}, v[2];
+    for (int i = 0; i < n; ++i) {
+        const pd_decoder *u = D->units.empty() ? D : D->units[i];
+        CUDA_TRY(cudaSetDevice(u->device));
+        CUDA_TRY(cudaMemcpy(v, dev_counters[i], sizeof v, cudaMemcpyDeviceToHost));
+        tot[0] += v[0]; tot[1] += v[1];
+    }
+    for (int i = 0; i < n; ++i) {
+        const pd_decoder *u = D->units.empty() ? D : D->units[i];
+        CUDA_TRY(cudaSetDevice(u->device));
+        CUDA_TRY(cudaMemcpy(dev_counters[i], tot, sizeof tot, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaSetDevice(D->device));
     return PD_OK;
 }
 
@@ -564,7 +776,8 @@ int pd_decode_device(pd_decoder *D, const void *dev_in, int in_dtype, int64_t B,
     static const int force_split = getenv("POLAR_B200_FORCE_SPLIT") ? atoi(getenv("POLAR_B200_FORCE_SPLIT")) : -1;
     const bool split = force_split == 0 ? false : (wave > 0 && B >= (force_split == 1 ? 4 : 8) * wave && ((N * esz) % 16 == 0));
     const int pieces = split ? kSplit : 1;
-    const int64_t per = split ? (((B + kSplit - 1) / kSplit + 31) & ~(int64_t)31) : B;
+    // pieces are whole waves of the persistent kernel (every warp of a piece runs the same number of passes)
+    const int64_t per = split ? ((((B + wave - 1) / wave) + kSplit - 1) / kSplit) * wave : B;
     // workspace: one region per concurrently running piece
     const size_t need1 = ws_need(D, in_dtype, dev_in, per);
     const size_t need = need1 * (split ? 2 : 1);
@@ -613,6 +826,12 @@ int pd_check(pd_decoder *D, void *cuda_stream) {
     if (!D) return fail(PD_EINVAL, "null decoder");
     CUDA_TRY(cudaSetDevice(D->device));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    if (*D->h_err & 0x40000000) {      // POLAR_B200_NO_TMA=2 (debug): a ring chunk differed from the stream
+        const int v = *D->h_err;
+        *D->h_err = 0;
+        return fail(PD_ECUDA, "ring check: chunk %d warp %d lane %d differs from the stream%s%s", v & 0xffff, (v >> 16) & 7, (v >> 19) & 31,
+                    (v & 0x20000000) ? " [holds the previous round's chunk: read too early]" : "", (v & 0x10000000) ? " [holds the next round's chunk: overwritten too early]" : "");
+    }
     if (*D->h_err) {
         *D->h_err = 0;
         return fail(PD_ERANGE, "an input symbol is outside the root lookup table (valid: [0,%d) for the first half, [0,%d) for the second)", D->dev.root_qa, D->dev.root_qb);
@@ -713,28 +932,101 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
         memcpy(host_out, D->h_small + kSmallIn, (size_t)B * Ko);
         return PD_OK;
     }
-    // pipeline chunk: ~16 MB of input (two streams alternate, so copies of one chunk hide behind the kernel of the other
-    // and the tail of one persistent launch overlaps the head of the next)
-    const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(8192, (int64_t)((16u << 20) / (N * esz))));
-    for (auto &sl : D->slot) {
-        if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        size_t in_need = (size_t)chunk * N * esz, out_need = (size_t)chunk * Ko;
-        if (sl.in_cap < in_need) { cudaFree(sl.d_in); sl.d_in = nullptr; sl.in_cap = 0; CUDA_TRY(cudaMalloc(&sl.d_in, in_need)); sl.in_cap = in_need; }
-        if (sl.out_cap < out_need) { cudaFree(sl.d_out); sl.d_out = nullptr; sl.out_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.d_out, out_need)); sl.out_cap = out_need; }
-        // our own staging buffers are cudaMalloc'ed (256-B aligned), so the kernel choice depends on the dtype only
-        size_t wsn = std::max(ws_need(D, in_dtype, nullptr, chunk), (size_t)16);
-        if (sl.ws_cap < wsn) { cudaFree(sl.ws); sl.ws = nullptr; sl.ws_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.ws, wsn)); sl.ws_cap = wsn; }
+    // pipeline chunk: ~16 MB of symbols, a whole number of kernel waves when the kernel is persistent.  Chunks are dealt
+    // round-robin to the decoder's units (pd_set_devices: this GPU and clones on others; default: this GPU alone), two
+    // stream slots per unit, so that the copies of one chunk hide behind the kernel of another.
+    std::vector<pd_decoder *> units = D->units.empty() ? std::vector<pd_decoder *>{D} : D->units;
+    const int U = (int)units.size();
+    const bool narrow = in_dtype == PD_I32 && D->fast.ok && D->force == 0;      // int32 symbols travel as bytes (4x less PCIe)
+    const size_t dsz = narrow ? 1 : esz;                                        // element size on the device
+    const int dev_dtype = narrow ? PD_U8 : in_dtype;
+    int64_t chunk = std::max<int64_t>(8192, (int64_t)((16u << 20) / (N * dsz)));
+    if (const int64_t wave = wave_frames(D, dev_dtype, nullptr)) chunk = std::max<int64_t>(1, (chunk + wave / 2) / wave) * wave;
+    if (const char *e = getenv("POLAR_B200_CHUNK_FRAMES")) chunk = std::max(1, atoi(e));      // (tests: force many small chunks)
+    chunk = std::min<int64_t>(B, chunk);
+    // the caller's buffers go through pinned staging memory unless they are pinned already (pd_host_alloc / cudaHostRegister):
+    // a cudaMemcpyAsync from pageable memory is neither asynchronous nor fast
+    const bool stage_in = narrow || !is_pinned(host_in), stage_out = !is_pinned(host_out);
+    for (pd_decoder *u : units) {
+        CUDA_TRY(cudaSetDevice(u->device));
+        for (auto &sl : u->slot) {
+            if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            if (!sl.done) CUDA_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+            size_t in_need = (size_t)chunk * N * dsz, out_need = (size_t)chunk * Ko;
+            if (sl.in_cap < in_need) { cudaFree(sl.d_in); sl.d_in = nullptr; sl.in_cap = 0; CUDA_TRY(cudaMalloc(&sl.d_in, in_need)); sl.in_cap = in_need; }
+            if (sl.out_cap < out_need) { cudaFree(sl.d_out); sl.d_out = nullptr; sl.out_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.d_out, out_need)); sl.out_cap = out_need; }
+            if (stage_in && sl.h_in_cap < in_need) { if (sl.h_in) cudaFreeHost(sl.h_in); sl.h_in = nullptr; sl.h_in_cap = 0; CUDA_TRY(cudaHostAlloc((void **)&sl.h_in, in_need, cudaHostAllocPortable)); sl.h_in_cap = in_need; }
+            if (stage_out && sl.h_out_cap < out_need) { if (sl.h_out) cudaFreeHost(sl.h_out); sl.h_out = nullptr; sl.h_out_cap = 0; CUDA_TRY(cudaHostAlloc((void **)&sl.h_out, out_need, cudaHostAllocPortable)); sl.h_out_cap = out_need; }
+            // our own staging buffers are cudaMalloc'ed (256-B aligned), so the kernel choice depends on the dtype only
+            size_t wsn = std::max(ws_need(u, dev_dtype, nullptr, chunk), (size_t)16);
+            if (sl.ws_cap < wsn) { cudaFree(sl.ws); sl.ws = nullptr; sl.ws_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.ws, wsn)); sl.ws_cap = wsn; }
+        }
     }
+    HostPool &pool = HostPool::get();
+    const int parts = pool.size();
+    std::atomic<int> bad_value{0};
+    const int n_slots = 2 * U;
+    std::vector<int64_t> pend_f0(n_slots, -1), pend_nb(n_slots, 0);
+    // waits for the chunk that occupies slot w (unit w % U, its slot w / U) and copies its result to the caller's output
+    auto drain = [&](int w) -> int {
+        if (pend_f0[w] < 0) return PD_OK;
+        pd_decoder *u = units[w % U];
+        StreamSlot &sl = u->slot[w / U];
+        CUDA_TRY(cudaSetDevice(u->device));
+        CUDA_TRY(cudaEventSynchronize(sl.done));     // the chunk's copies are done: both pinned areas of the slot are free again
+        if (stage_out) {
+            const size_t bytes = (size_t)pend_nb[w] * Ko, per = (bytes / parts + 63) & ~(size_t)63;
+            uint8_t *dst = host_out + (size_t)pend_f0[w] * Ko;
+            const char *src = sl.h_out;
+            pool.run(parts, [&](int i) {
+                const size_t o = (size_t)i * per;
+                if (o < bytes) memcpy(dst + o, src + o, std::min(per, bytes - o));
+            });
+        }
+        pend_f0[w] = -1;
+        return PD_OK;
+    };
     int which = 0;
-    for (int64_t f0 = 0; f0 < B; f0 += chunk, which ^= 1) {
-        StreamSlot &sl = D->slot[which];
-        int64_t nb = std::min<int64_t>(chunk, B - f0);
-        CUDA_TRY(cudaMemcpyAsync(sl.d_in, (const char *)host_in + (size_t)f0 * N * esz, (size_t)nb * N * esz, cudaMemcpyHostToDevice, sl.stream));
-        if ((rc = launch(D, sl.d_in, in_dtype, nb, sl.d_out, sl.stream, sl.ws))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)f0 * Ko, sl.d_out, (size_t)nb * Ko, cudaMemcpyDeviceToHost, sl.stream));
+    for (int64_t f0 = 0; f0 < B; f0 += chunk, which = (which + 1) % n_slots) {
+        pd_decoder *u = units[which % U];
+        StreamSlot &sl = u->slot[which / U];
+        const int64_t nb = std::min<int64_t>(chunk, B - f0);
+        if ((rc = drain(which))) return rc;          // the slot's previous chunk
+        CUDA_TRY(cudaSetDevice(u->device));
+        const void *h2d_src = (const char *)host_in + (size_t)f0 * N * esz;
+        if (stage_in) {
+            const size_t elems = (size_t)nb * N, per = ((elems / parts) + 63) & ~(size_t)63;
+            const char *src = (const char *)h2d_src;
+            char *dst = sl.h_in;
+            pool.run(parts, [&](int i) {
+                const size_t o = (size_t)i * per;
+                if (o >= elems) return;
+                const size_t n = std::min(per, elems - o);
+                if (narrow) { if (!narrow_i32_to_u8((const int32_t *)src + o, (uint8_t *)dst + o, n)) bad_value = 1; }
+                else memcpy(dst + o * esz, src + o * esz, n * esz);
+            });
+            h2d_src = sl.h_in;
+        }
+        CUDA_TRY(cudaMemcpyAsync(sl.d_in, h2d_src, (size_t)nb * N * dsz, cudaMemcpyHostToDevice, sl.stream));
+        if ((rc = launch(u, sl.d_in, dev_dtype, nb, sl.d_out, sl.stream, sl.ws))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(stage_out ? (void *)sl.h_out : (void *)(host_out + (size_t)f0 * Ko), sl.d_out, (size_t)nb * Ko, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaEventRecord(sl.done, sl.stream));
+        pend_f0[which] = f0; pend_nb[which] = nb;
     }
-    CUDA_TRY(cudaStreamSynchronize(D->slot[0].stream));
-    return pd_check(D, D->slot[1].stream);
+    for (int k = 0; k < n_slots; ++k, which = (which + 1) % n_slots)
+        if ((rc = drain(which))) return rc;
+    rc = PD_OK;
+    for (pd_decoder *u : units) {
+        CUDA_TRY(cudaSetDevice(u->device));
+        for (auto &sl : u->slot) {
+            const int r2 = pd_check(u, sl.stream);
+            if (r2 != PD_OK && rc == PD_OK) rc = r2;
+        }
+    }
+    CUDA_TRY(cudaSetDevice(D->device));
+    if (rc == PD_OK && bad_value.load())
+        return fail(PD_ERANGE, "an input symbol is outside the root lookup table (valid: [0,%d) for the first half, [0,%d) for the second)", D->dev.root_qa, D->dev.root_qb);
+    return rc;
 }
 
 #ifndef PB_HOST_EMU

@@ -194,7 +194,7 @@ __device__ __forceinline__ double dev_bisect(double a, const double *boundary, i
         int mid = (lo + hi) / 2;
         if (boundary[mid] < a) lo = mid + 1; else hi = mid;
     }
-    return rec[lo - 1];
+    return rec[lo > 0 ? lo - 1 : 0];   // (pd_create guarantees boundary[0] = -inf-like and nr >= nb-1; NaN input: first cell)
 }
 
 struct Ctl {
@@ -280,7 +280,7 @@ generic_decode_kernel(const Dev d, const void *__restrict__ in, int in_dtype, ui
     // carve the per-CTA workspace
     char *base = use_smem ? dyn_smem : ws + (size_t)blockIdx.x * ws_stride;
     T *V = reinterpret_cast<T *>(base);
-    size_t off = (size_t)L * VS * sizeof(T);
+    size_t off = ((size_t)L * VS * sizeof(T) + 15) & ~(size_t)15;   // (uint8 values: keep the fp64 scratch behind them aligned)
     double *AL = reinterpret_cast<double *>(base + off);       // R1 scratch: |llr| rows
     off += (size_t)L * d.r1_tmax * sizeof(double);
     int *SI = reinterpret_cast<int *>(base + off);              // R1 scratch: argsort rows

@@ -558,7 +558,8 @@ inline void plan_path_warp(const Dev &d, PathPlan *pl) {
     pl->logL = logL;
     const void *fn = path_kernel_fn(d.domain, logL);
     if (pl->smem > 160 * 1024) return;
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess) { cudaGetLastError(); return; }
+    // (per-function state shared by every decoder of this domain and list size: always the cap, see plan_generic)
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) { cudaGetLastError(); return; }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, pl->smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return; }
     pl->ctas_per_sm = occ;

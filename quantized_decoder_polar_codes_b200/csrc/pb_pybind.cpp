@@ -10,9 +10,12 @@
 //   * LUT_f / LUT_g entries may be given as one [Qa][Qb] / [2][Qa][Qb] table per node.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -100,6 +103,51 @@ void flatten_llr(const py::object &llr, int N, Tables &t) {
         }
     }
 }
+
+// Large decode() results live in pinned host memory (pd_host_alloc): the device->host copy then lands in the numpy array
+// itself instead of going through a staging area.  A few buffers are recycled (pinning is slow); the array's capsule hands
+// its buffer back when numpy frees the array.
+namespace {
+struct PinnedPool {
+    std::mutex m;
+    std::vector<std::pair<void *, size_t>> free_;
+    void *get(size_t n, size_t *cap) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].second >= n && free_[i].second <= 2 * n + (1u << 20)) {
+                    void *p = free_[i].first;
+                    *cap = free_[i].second;
+                    free_.erase(free_.begin() + (long)i);
+                    return p;
+                }
+        }
+        *cap = n;
+        return pd_host_alloc(n);
+    }
+    void put(void *p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            if (free_.size() < 4) { free_.emplace_back(p, cap); return; }
+        }
+        pd_host_free(p);
+    }
+};
+PinnedPool &pinned_pool() { static PinnedPool *p = new PinnedPool(); return *p; }   // (never destroyed: no CUDA calls at exit)
+struct PinnedBlock { void *p; size_t cap; };
+
+py::array_t<uint8_t> result_array(int64_t B, int ko, bool flat) {
+    const size_t bytes = (size_t)B * (size_t)ko;
+    static const size_t min_bytes = getenv("POLAR_B200_PINNED_RESULT_MIN") ? (size_t)atoll(getenv("POLAR_B200_PINNED_RESULT_MIN")) : (size_t)(4u << 20);
+    if (flat || bytes < min_bytes) return flat ? py::array_t<uint8_t>(ko) : py::array_t<uint8_t>({(py::ssize_t)B, (py::ssize_t)ko});
+    size_t cap = 0;
+    void *p = pinned_pool().get(bytes, &cap);
+    if (!p) return py::array_t<uint8_t>({(py::ssize_t)B, (py::ssize_t)ko});
+    auto *blk = new PinnedBlock{p, cap};
+    py::capsule owner(blk, [](void *v) { auto *b = static_cast<PinnedBlock *>(v); pinned_pool().put(b->p, b->cap); delete b; });
+    return py::array_t<uint8_t>({(py::ssize_t)B, (py::ssize_t)ko}, {(py::ssize_t)ko, (py::ssize_t)1}, static_cast<uint8_t *>(p), owner);
+}
+}  // namespace
 
 class Decoder {
 public:
@@ -192,10 +240,11 @@ public:
         } else {
             throw py::value_error("decode: expected shape (N,), (1,N) or (B,N)");
         }
-        py::array_t<uint8_t> out = flat ? py::array_t<uint8_t>(ko) : py::array_t<uint8_t>({(py::ssize_t)B, (py::ssize_t)ko});
+        py::array_t<uint8_t> out = result_array(B, ko, flat);
         int rc;
         {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::mutex> one_call_at_a_time(mu_);   // the C ABI object is not re-entrant; the reference (GIL held) was
             rc = pd_decode(dec_, arr.data(), dtype, B, out.mutable_data());
         }
         if (rc != PD_OK) raise_status(rc);
@@ -224,6 +273,7 @@ public:
         int rc;
         {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::mutex> one_call_at_a_time(mu_);   // the C ABI object is not re-entrant; the reference (GIL held) was
             rc = pd_decode_bd(dec_, arr.data(), B, nullptr, 0, nullptr, metric.mutable_data(), nullptr);
         }
         if (rc != PD_OK) raise_status(rc);
@@ -242,6 +292,7 @@ public:
         int rc;
         {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::mutex> one_call_at_a_time(mu_);   // the C ABI object is not re-entrant; the reference (GIL held) was
             rc = pd_decode_bd(dec_, arr.data(), B, r.data(), (int32_t)r.size(), bits.mutable_data(), pm.mutable_data(), pass.mutable_data());
         }
         if (rc != PD_OK) raise_status(rc);
@@ -249,11 +300,19 @@ public:
         return py::make_tuple(bits, pm, pass.attr("astype")("bool"));
     }
 
+    // decode() deals its batch to these CUDA devices from now on (pd_set_devices); [] = the constructor's device alone
+    void set_devices(const std::vector<int32_t> &ids) {
+        std::lock_guard<std::mutex> one_call_at_a_time(mu_);
+        const int rc = pd_set_devices(dec_, (int32_t)ids.size(), ids.data());
+        if (rc != PD_OK) raise_status(rc);
+    }
+    int device_count() const { return pd_device_count(dec_); }
     std::string kernel() const { return pd_kernel_name(dec_); }
     uintptr_t handle() const { return reinterpret_cast<uintptr_t>(dec_); }
 
 private:
     pd_decoder *dec_ = nullptr;
+    std::mutex mu_;
     int N_ = 0;
     bool lut_ = false;
 };
@@ -268,6 +327,8 @@ py::class_<Cls<KIND>> declare(py::module_ &m, const char *name, const char *doc,
     py::class_<Cls<KIND>> c(m, name, doc);
     c.def("decode", &Decoder::decode, py::arg(decode_arg));
     c.def_property_readonly("kernel", &Decoder::kernel, "name of the CUDA kernel variant in use");
+    c.def("set_devices", &Decoder::set_devices, py::arg("device_ids"), "shard every decode() call over these CUDA devices of the box (pd_set_devices)");
+    c.def_property_readonly("device_count", &Decoder::device_count);
     c.def_property_readonly("_handle", &Decoder::handle, "pd_decoder* for direct C-ABI calls");
     return c;
 }

@@ -65,6 +65,7 @@ struct FastParams {
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
     int warps;                     // consumer warps per CTA; one more warp streams the tables
+    int no_tma;                    // debug knob (POLAR_B200_NO_TMA): the producer warp copies the stages with plain loads / stores
     int warp_words;                // shared-memory words of one consumer warp (its V, X, scratch, fork cells)
     int vwords, xwords, scrwords;  // shared-memory words per lane: value levels gl+1..top, X; scratch words per warp
     int scr_off;                   // word offset of the epilogue scratch: its own region, or 0 = on top of the (then dead) value levels
@@ -117,8 +118,9 @@ __device__ __forceinline__ void mbar_init(smaddr_t b, unsigned count) { asm vola
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(smaddr_t b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory"); }
 __device__ __forceinline__ void mbar_wait(smaddr_t b, unsigned parity) {   // returns once the phase of that parity is complete
-    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
-                 ::"r"(b), "r"(parity) : "memory");
+    // (the third operand is a suspend-time hint: the waiting warp sleeps in hardware instead of spinning on issue slots)
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+                 ::"r"(b), "r"(parity), "r"(0x989680u) : "memory");
 }
 // one TMA bulk copy global -> shared; `bar` receives the single arrival and the byte count
 __device__ __forceinline__ void bulk_load(smaddr_t dst, const void *gsrc, unsigned bytes, smaddr_t bar) {
@@ -212,14 +214,36 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     const int n_pass = first < n_groups ? (int)((n_groups - first + per_pass - 1) / per_pass) : 0;
     const uint32_t spp = (uint32_t)fp.n_chunks / kCPS;        // stages per pass (the stream is padded to whole stages)
     if (wid == W) {                                           // ---- producer warp
-        if (lane == 0) {
+        if (fp.no_tma) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(fp.stream);
+            uint4 *ring4 = reinterpret_cast<uint4 *>(RINGB);
+            uint32_t i = 0;
+            for (int p = 0; p < n_pass; ++p)
+                for (uint32_t s = 0; s < spp; ++s, ++i) {
+                    const uint32_t st = i & (kStages - 1);
+                    mbar_wait(bars + (kStages + st) * 8u, ((i / kStages) & 1u) ^ 1u);
+                    for (int k = lane; k < (int)(kStageBytes / 16); k += 32) ring4[st * (kStageBytes / 16) + k] = __ldg(src + (size_t)s * (kStageBytes / 16) + k);
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars + st * 8u);
+                }
+            return;
+        }
+        // TMA producer.  The WHOLE warp stays in the loop and lane 0 issues: with lanes 1..31 retired and lane 0 left alone
+        // to wait and issue, the L = 1 kernels stopped (or faulted) as soon as an SM held its full complement of CTAs --
+        // measured on B200, round 2 (profiles/r2/README.md); the copy loop of a full warp (POLAR_B200_NO_TMA=1) and this
+        // form both run every shape.
+        {
             const char *src = reinterpret_cast<const char *>(fp.stream);
             uint32_t i = 0;
             for (int p = 0; p < n_pass; ++p)
                 for (uint32_t s = 0; s < spp; ++s, ++i) {
                     const uint32_t st = i & (kStages - 1);
-                    mbar_wait(bars + (kStages + st) * 8u, ((i / kStages) & 1u) ^ 1u);     // slot free (passes at once the first time round)
-                    bulk_load(ring0 + st * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bars + st * 8u);
+                    if (lane == 0) {
+                        mbar_wait(bars + (kStages + st) * 8u, ((i / kStages) & 1u) ^ 1u);     // slot free (passes at once the first time round)
+                        bulk_load(ring0 + st * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bars + st * 8u);
+                    }
+                    __syncwarp();
                 }
         }
         return;
@@ -241,6 +265,25 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     // the Fast-SSC variant has ~40 consumption sites: there the stream accessors are real (out-of-line) functions so
     // that the hot code stays inside the instruction cache; the plain variant inlines them
     auto next_chunk = [&]() -> uint4 {
+#ifdef PB_RING_VERIFY
+        if (fp.no_tma == 2) {   // debug build only: check every chunk read from the ring against the stream in global memory
+            const uint32_t c0 = ls.cc;
+            uint4 v = ring_next_chunk(ls.cc, ring_lane, bars, lane);
+            const uint32_t nch = (uint32_t)fp.n_chunks, k = c0 % nch;
+            const uint4 *gs = reinterpret_cast<const uint4 *>(fp.stream);
+            const uint4 e = __ldg(gs + (size_t)k * 32 + lane);
+            if (v.x != e.x || v.y != e.y || v.z != e.z || v.w != e.w) {
+                const uint4 prev = __ldg(gs + (size_t)((k + nch - kRingSlots % nch) % nch) * 32 + lane);
+                const uint4 nxt = __ldg(gs + (size_t)((k + kRingSlots) % nch) * 32 + lane);
+                int code = 0x40000000;
+                if (v.x == prev.x && v.y == prev.y && v.z == prev.z && v.w == prev.w) code |= 0x20000000;   // stale: the previous round's chunk
+                if (v.x == nxt.x && v.y == nxt.y && v.z == nxt.z && v.w == nxt.w) code |= 0x10000000;       // overwritten early: the next round's chunk
+                atomicOr(err_flag, code | (int)(c0 & 0xffffu) | ((wid & 7) << 16) | ((lane & 31) << 19));
+                v = e;
+            }
+            return v;
+        }
+#endif
         if (FAST && L > 1) {
             const uint4 v = ring_fetch_outlined(ls.cc, ring_lane, bars, lane);
             ++ls.cc;
@@ -1284,6 +1327,8 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     }
     if (best_w < 1 || best_occ < 1) { free_fast_plan(pl); return; }
     P.warps = best_w;
+    P.no_tma = getenv("POLAR_B200_NO_TMA") ? atoi(getenv("POLAR_B200_NO_TMA")) : 0;
+    if (const char *e = getenv("POLAR_B200_CTAS_PER_SM")) best_occ = std::max(1, std::min(best_occ, atoi(e)));   // tuning / debug knob
     pl->smem = (size_t)best_w * P.warp_words * 4 + ring_bytes;
     pl->ws_bytes_per_cta = (size_t)P.gwords * 32 * 4 * best_w;
     pl->ctas_per_sm = best_occ;

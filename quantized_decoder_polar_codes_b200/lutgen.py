@@ -278,3 +278,20 @@ def mmi_channel_quantizer(sigma, q_uniform=128, q_channel=16, device=0):
         pzx[0, i] = np.sum(pyx1[channel_lut[i]:channel_lut[i + 1]])
         pzx[1, i] = np.sum(pyxm[channel_lut[i]:channel_lut[i + 1]])
     return pzx, interval_x, channel_lut
+
+
+def channel_llr_density_table(M, low, high, mu1, mu2, sigma):
+    """utils.py:30-44 of the reference: density and centroid of M uniform LLR cells on [low, high] under the equiprobable
+    mixture N(mu1, sigma^2) / N(mu2, sigma^2), integrated on a 1e-4 grid like channel_transition_probability_table."""
+    delta = 0.0001
+    x = np.arange(low, high + delta, delta)
+    pdf = 0.5 * (1 / np.sqrt(2 * np.pi * sigma ** 2) * np.exp(-(x - mu1) ** 2 / (2 * sigma ** 2)) +
+                 1 / np.sqrt(2 * np.pi * sigma ** 2) * np.exp(-(x - mu2) ** 2 / (2 * sigma ** 2)))
+    edges = np.linspace(low, high, M + 1)
+    quanta, pyx = np.zeros(M), np.zeros(M)
+    for i in range(M):
+        sel = np.bitwise_and(x >= edges[i], x <= edges[i + 1])
+        d = pdf[sel]
+        pyx[i] = np.sum(d) * delta
+        quanta[i] = np.sum(x[sel] * d) / np.sum(d)
+    return pyx, edges, quanta

@@ -23,6 +23,9 @@ class Simulator:
         self.N = self.lib.pd_code_len(decoder._handle)
         self.kout = self.lib.pd_out_len(decoder._handle)
         self.A = int(A)
+        if self.kout != self.A:
+            raise ValueError(f"the decoder returns {self.kout} bits per frame but the messages have A={self.A}: with a CRC use a "
+                             "CRC-aided class (it returns the A message bits); pd_count_errors compares [B][A] rows")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         fb = np.ascontiguousarray(frozen_bits, dtype=np.int32)
         K = int((fb == 0).sum())

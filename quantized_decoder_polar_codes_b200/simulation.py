@@ -44,6 +44,131 @@ def frozen_mask(N, K, construction="nr"):
     return fm, (1 - fm).astype(np.int32)
 
 
+def _ga_phi(x):
+    """CodeConstruction.py:38-49 (Chung's approximation; note the exponent 0.859 here and 0.86 in the inverse -- kept)."""
+    if 0 <= x <= 10:
+        return np.exp(-0.4527 * np.power(x, 0.859) + 0.0218)
+    return np.sqrt(np.pi / x) * np.exp(-x / 4) * (1 - 10 / 7 / x)
+
+
+def _ga_dphi(x):
+    """CodeConstruction.py:3-13"""
+    if 0 <= x <= 10:
+        return -0.4527 * 0.86 * np.power(x, -0.14) * _ga_phi(x)
+    return np.exp(-x / 4) * np.sqrt(np.pi / x) * (-1 / 2 / x * (1 - 10 / 7 / x) - 1 / 4 * (1 - 10 / 7 / x) + 10 / 7 / x / x)
+
+
+def _ga_phi_inverse(x):
+    """CodeConstruction.py:15-36: closed form on [0.0388, 1.0221], Newton iteration elsewhere (same start, same stop rule)."""
+    if 0.0388 <= x <= 1.0221:
+        return np.power((0.0218 - np.log(x)) / 0.4527, 1 / 0.86)
+    x0 = 0.0388
+    x1 = x0 - (_ga_phi(x0) - x) / _ga_dphi(x0)
+    delta, eps = abs(x1 - x0), 1e-3
+    while delta >= eps:
+        x0 = x1
+        x1 = x1 - (_ga_phi(x1) - x) / _ga_dphi(x1)
+        if x1 > 1e2:
+            eps = 10
+        delta = abs(x1 - x0)
+    return x1
+
+
+def _bitreverse(x):
+    """CodeConstruction.py:51-61"""
+    if len(x) == 1:
+        return x
+    return np.concatenate([_bitreverse(x[0::2]), _bitreverse(x[1::2])])
+
+
+def frozen_mask_ga(N, K, sigma):
+    """Gaussian-approximation construction, PolarCodeConstructor.GA(sigma) (CodeConstruction.py:86-115): mean LLR of every bit
+    channel by the f / g recursions, the K largest (after the reference's bit reversal of the leaf order) carry information.
+    Used for N = 2048 (BASELINE config 5): the NR reliability table stops at 1024.
+    -> (frozen_mask int32[N], message_mask int32[N])."""
+    n = int(np.log2(N))
+    u = np.zeros((n + 1, N))
+    u[0, :] = 2 / sigma ** 2
+    for level in range(1, n + 1):
+        nb_parent = 2 ** (n - level + 1)
+        nb = nb_parent // 2
+        for node in range(2 ** (level - 1)):
+            tmp = u[level - 1, nb_parent * node]
+            f = _ga_phi_inverse(1 - (1 - _ga_phi(tmp)) ** 2)
+            g = 2 * tmp
+            u[level, 2 * node * nb:(2 * node + 1) * nb] = f
+            u[level, (2 * node + 1) * nb:(2 * node + 2) * nb] = g
+    order = np.argsort(_bitreverse(u[-1, :]))
+    fm = np.zeros(N, np.int32)
+    fm[order[: N - K]] = 1
+    return fm, (1 - fm).astype(np.int32)
+
+
+def _uq_dr(mu, sigma2, v, r):
+    """derivative of the uniform quantizer's distortion w.r.t. its step r for the mixture N(mu,s2)/2 + N(-mu,s2)/2
+    (OptUniformQuantizerGaussian.py:76-101: dr_middle / dr_last / dr_bimodal_Gaussian, same order of operations)"""
+    from scipy.special import erf
+
+    def gauss(m, x):
+        return 1 / np.sqrt(2 * np.pi * sigma2) * np.exp(-(x - m) ** 2 / (2 * sigma2))
+
+    def middle(a, b, rv):
+        p1 = -sigma2 / 2 * (gauss(mu, b) - gauss(mu, a))
+        p2 = 0.25 * (mu - rv) * (erf((b - mu) / (np.sqrt(2 * sigma2))) - erf((a - mu) / (np.sqrt(2 * sigma2))))
+        p3 = -sigma2 / 2 * (gauss(-mu, b) - gauss(-mu, a))
+        p4 = 0.25 * (-mu - rv) * (erf((b - -mu) / (np.sqrt(2 * sigma2))) - erf((a - -mu) / (np.sqrt(2 * sigma2))))
+        return 2 * (p1 + p2 + p3 + p4)
+
+    def last(a, rv):
+        p1 = sigma2 / 2 * gauss(mu, a) + 0.25 * (mu - rv) * (1 - erf((a - mu) / (np.sqrt(2 * sigma2))))
+        p2 = sigma2 / 2 * gauss(-mu, a) + 0.25 * (-mu - rv) * (1 - erf((a - -mu) / (np.sqrt(2 * sigma2))))
+        return 2 * (p1 + p2)
+
+    result = 0
+    half = v // 2
+    for k in range(1, half):
+        result -= (2 * k - 1) * middle((k - 1) * r, k * r, (k - 1 / 2) * r)
+    result -= (2 * half - 1) * last((half - 1) * r, (half - 1 / 2) * r)
+    return result
+
+
+def _uq_opt_step(mu, sigma2, v, max_iter=30):
+    """OptUniformQuantizerGaussian.find_optimal_interval_bimodal_Gaussian (:134-149): Newton iteration on dr, second
+    derivative by central differences (delta 1e-6), stop when dr moves by < 1e-6."""
+    r = 2 * (mu + 3 * np.sqrt(sigma2) - (-mu - 3 * np.sqrt(sigma2))) / (v - 2)
+    for _ in range(max_iter):
+        d2r = (_uq_dr(mu, sigma2, v, r + 1e-6) - _uq_dr(mu, sigma2, v, r - 1e-6)) / (2 * 1e-6)
+        dr = _uq_dr(mu, sigma2, v, r)
+        r -= dr / d2r
+        if np.abs(_uq_dr(mu, sigma2, v, r) - dr) < 1e-6:
+            break
+    return r
+
+
+def uniform_quantizer_steps(N, v, sigma):
+    """LLRLSUniformQuantizer(N, v).generate_uniform_quantizers(sigma) (QLLRDensityEvolution_OptUniform.py:11-36): the step sizes
+    decoder_r_f / decoder_r_g [N-1] (heap order) the continuous-domain driver hands to the uniformly quantized decoders
+    (mainQuantizedDecoder_ContinuousDomain.py:99-104) -- Gaussian approximation of the LLR mean per node, optimal uniform step
+    for the resulting +-mu mixture with variance 2 mu."""
+    n = int(np.log2(N))
+    mu_llr = np.zeros((n + 1, N))
+    mu_llr[0, :] = 2 / sigma ** 2
+    r_f, r_g = np.zeros(N - 1), np.zeros(N - 1)
+    for level in range(1, n + 1):
+        nb_parent = 2 ** (n - level + 1)
+        nb = nb_parent // 2
+        for node in range(2 ** (level - 1)):
+            p = 2 ** (level - 1) - 1 + node
+            mu = mu_llr[level - 1, nb_parent * node]
+            mu_f = _ga_phi_inverse(1 - (1 - _ga_phi(mu)) ** 2)
+            r_f[p] = _uq_opt_step(mu_f, 2 * mu_f, v)
+            mu_g = 2 * mu
+            r_g[p] = _uq_opt_step(mu_g, 2 * mu_g, v)
+            mu_llr[level, 2 * node * nb:(2 * node + 1) * nb] = mu_f
+            mu_llr[level, (2 * node + 1) * nb:(2 * node + 2) * nb] = mu_g
+    return r_f, r_g
+
+
 def identify_nodes(N, frozen, spc=True):
     """Fast-SSC node classification (IdentifyNodes.py:13-150 with use_new_node=False).
     -> int32[2N-1] indexed by heap id (1<<depth)+node-1: -1 ordinary, 0 R0, 1 R1, 2 REP, 3 SPC.

@@ -189,7 +189,7 @@ def test_north_star_workload_of_the_benchmark(q):
     generator code) and the driver's channel quantizer at 2 dB -- bit-exact vs the oracle (which equals the compiled
     reference on these tables, tests/test_oracle.py), and a sane BLER."""
     import bench
-    kw, sym, msg = bench.make_workload(600, seed=3)
+    kw, sym, msg = bench.make_workload(bench.CONFIGS["NS"], 600, seed=3)
     dec = q.SCLLUTDecoder(**kw)
     assert dec.kernel == "scl_lut_warp"
     got = dec.decode(sym)
@@ -298,3 +298,82 @@ def test_properties_at_full_size(q):
     sub = np.arange(0, 20000, 400)
     want = po.OracleDecoder("SCLLUTDecoder", **kw).decode(x[sub])
     assert (y[sub] == want).all()
+
+
+@pytest.mark.parametrize("kind,force", [("SCLLUTDecoder", 0), ("SCLDecoder", 0), ("SCLLUTDecoder", 1), ("SCLDecoder", 1)])
+def test_large_decoder_survives_a_smaller_one_created_later(monkeypatch, kind, force):
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel function, shared by every decoder of the family:
+    an N=128 decoder created after an N=1024 one must not shrink the cap under the live larger decoder."""
+    import quantized_decoder_polar_codes_b200 as q
+    if force:
+        monkeypatch.setenv("POLAR_B200_FORCE_GENERIC", "1")
+    tab = dict(tables="minsum") if "LUT" in kind else dict(tables="channel")
+    kw_big, x_big, _ = common.make_case(kind, N=1024, K=512, L=4, B=16, seed=5, **tab)
+    kw_small, x_small, _ = common.make_case(kind, N=128, K=64, L=4, B=16, seed=6, **tab)
+    big = getattr(q, kind)(**kw_big)
+    first = big.decode(x_big)
+    small = getattr(q, kind)(**kw_small)
+    small.decode(x_small)
+    again = big.decode(x_big)          # used to fail with "invalid argument" once the cap had shrunk
+    assert (first == again).all()
+    assert (first == po.OracleDecoder(kind, **kw_big).decode(x_big)).all()
+
+
+@pytest.mark.parametrize("kind,N,K,L,B", [("SCLUTDecoder", 256, 128, 1, 1 << 19), ("SCLUTDecoder", 1024, 512, 1, 113664 + 32),
+                                           ("FastSCLUTDecoder", 1024, 512, 1, 1 << 17), ("SCLLUTDecoder", 512, 256, 4, 1 << 17)])
+def test_full_residency_batches(q, kind, N, K, L, B):
+    """Batches that fill every SM with its full complement of CTAs (and a few passes more).  Round 2 found the L = 1 kernels
+    hanging exactly there while every small-batch test passed (consumer warps suspended in mbarrier.try_wait on a barrier
+    completed by a TMA transaction; they poll with test_wait now)."""
+    import torch
+    from quantized_decoder_polar_codes_b200 import capi
+    kw, x, _ = common.make_case(kind, N=N, K=K, L=L, B=2048, seed=9, tables="minsum", ebn0_db=3.0)
+    want = po.OracleDecoder(kind, **kw).decode(x[:256].astype(np.int32))
+    reps = -(-B // 2048)
+    xs = np.tile(x.astype(np.uint8), (reps, 1))[:B]
+    dec = getattr(q, kind)(**kw)
+    d_in = torch.from_numpy(xs).cuda()
+    d_out = torch.empty((B, want.shape[1]), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        capi.decode_device(dec, d_in.data_ptr(), capi.PD_U8, B, d_out.data_ptr(), s)
+    capi.sync_check(dec, s)
+    got = d_out.cpu().numpy()
+    assert (got[:256] == want).all()
+    last = (B // 2048 - 1) * 2048                      # the last full copy of the 2048 unique frames
+    assert (got[last:last + 256] == want).all()
+    assert (got[:2048] == got[last:last + 2048]).all()
+
+
+@pytest.mark.parametrize("dtype", ["int32", "uint8", "float64", "int64"])
+def test_host_call_staging_paths(q, monkeypatch, dtype):
+    """decode((B,N)) from pageable numpy memory in the dtypes the drivers use: int32 symbols are narrowed to bytes on the host
+    (thread pool -> pinned staging -> H2D), results come back in a pinned array; many small chunks to turn the pipeline over."""
+    monkeypatch.setenv("POLAR_B200_CHUNK_FRAMES", "3000")
+    kw, x, _ = common.make_case("SCLLUTDecoder", N=256, K=128, L=4, B=20000, seed=12)
+    dec = q.SCLLUTDecoder(**kw)
+    got = dec.decode(x.astype(dtype))
+    want = po.OracleDecoder("SCLLUTDecoder", **kw).decode(x.astype(np.int32))
+    assert got.shape == want.shape and (got == want).all()
+    bad = x.astype(np.int32).copy()
+    bad[12345 % bad.shape[0], 7] = 300                  # does not fit a byte: must be reported, not truncated to 44
+    with pytest.raises(ValueError):
+        dec.decode(bad)
+    assert (dec.decode(x.astype(dtype)) == want).all()  # and the decoder stays usable
+
+
+def test_set_devices_shards_one_call(q, monkeypatch):
+    """pd_set_devices: one decode() call dealt to several pipelines (here: three on the one visible GPU; the same code path
+    deals to several GPUs) returns what a single device returns; [] restores the single-device path."""
+    import torch
+    monkeypatch.setenv("POLAR_B200_CHUNK_FRAMES", "2500")
+    kw, x, _ = common.make_case("CASCLLUTDecoder", N=256, K=152, A=128, L=8, B=16000, seed=13)
+    dec = q.CASCLLUTDecoder(**kw)
+    want = dec.decode(x)
+    ids = [0, 0, 0] if torch.cuda.device_count() < 2 else [0, 1, 0, 1]
+    dec.set_devices(ids)
+    assert dec.device_count == len(ids)
+    assert (dec.decode(x) == want).all()
+    dec.set_devices([])
+    assert dec.device_count == 1 and (dec.decode(x) == want).all()
+    assert (want[:64] == po.OracleDecoder("CASCLLUTDecoder", **kw).decode(x[:64])).all()

@@ -136,10 +136,58 @@ def test_north_star_scl_lut_n1024(q, ebn0):
     _check(q, "NS SCL-LUT N=1024 A=512 L=8", "SCLLUTDecoder", kw, x, msg, ebn0)
 
 
+def mmi_channel_frames(N, K, A, ebn0_db, frames, seed, edges, Q=16):
+    """probability-domain driver (mainQuantizedDecoder_ProbabilityDomain.py:153-177): y = BPSK + noise is cut at the MMI channel
+    quantizer's edges interval_x[channel_lut] with utils.continous2discret (<= first edge -> 0, >= last -> Q-1, else
+    bisect_left - 1); the symbols are handed over as float64."""
+    rng = np.random.default_rng(seed)
+    fm, _ = sim.frozen_mask(N, K)
+    msg = rng.integers(0, 2, (frames, A), dtype=np.uint8)
+    cw = sim.polar_encode(sim.crc_attach(msg) if K > A else msg, fm)
+    sigma = sim.awgn_sigma(ebn0_db, A / N)
+    y = (1.0 - 2.0 * cw) + rng.normal(0.0, sigma, cw.shape)
+    idx = np.searchsorted(edges, y, side="left") - 1
+    sym = np.where(y <= edges[0], 0, np.where(y >= edges[-1], Q - 1, idx))
+    return sym.astype(np.float64), msg
+
+
+def _n1024_mmi_tables():
+    z = np.load(os.path.join(ROOT, "quantized_decoder_polar_codes_b200", "data", "mmi_n1024_q16_3dB.npz"))
+    f = [z["lut_f"][p].astype(np.int32)[None] for p in range(1023)]
+    g = [z["lut_g"][p].astype(np.int32)[None] for p in range(1023)]
+    return z, f, g
+
+
+@pytest.mark.parametrize("ebn0", [1, 2, 3] if FULL else [2])
+def test_c4_ca_fast_scl_lut_n1024_mmi_tables(q, ebn0):
+    """C4 as BASELINE.json names it: MMI tables (probability domain: virtual_channel_llr has n levels, symbols arrive as
+    float64), CAFastSCLLUTDecoder N=1024, A=512 + CRC-24 (K=536), L=8.  The tables come from this package's MMI generator
+    (tools/make_mmi_n1024.py; bit-identical to the reference generator on the golden sizes, tests/test_mmi_lutgen.py)."""
+    N, A, K = 1024, 512, 536
+    z, f, g = _n1024_mmi_tables()
+    fm, mm = sim.frozen_mask(N, K)
+    kw = dict(N=N, K=K, A=A, L=8, frozen_bits=fm, message_bits=mm, node_type=sim.identify_nodes(N, fm), LUT_f=f, LUT_g=g,
+              virtual_channel_llr=z["llrs"])
+    x, msg = mmi_channel_frames(N, K, A, ebn0, 20_000 if FULL else 1_200, seed=400 + ebn0, edges=z[f"chan_A512_eb{ebn0}/edges"])
+    _check(q, "C4 MMI CAFastSCL-LUT N=1024 A=512 K=536 L=8", "CAFastSCLLUTDecoder", kw, x, msg, ebn0)
+
+
+@pytest.mark.parametrize("kind", ["FastSCLLUTDecoder", "SCLLUTDecoder"])
+def test_mmi_tables_n1024_other_list_decoders(q, kind):
+    """the probability-domain driver's own list decoders (it has no CRC-aided Fast class) on the same tables"""
+    N, K = 1024, 512
+    z, f, g = _n1024_mmi_tables()
+    fm, mm = sim.frozen_mask(N, K)
+    kw = dict(N=N, K=K, L=8, frozen_bits=fm, message_bits=mm, LUT_f=f, LUT_g=g, virtual_channel_llr=z["llrs"])
+    if "Fast" in kind:
+        kw["node_type"] = sim.identify_nodes(N, fm)
+    x, msg = mmi_channel_frames(N, K, K, 2, 2_000 if FULL else 600, seed=450, edges=z["chan_A512_eb2/edges"])
+    _check(q, "MMI " + kind + " N=1024 A=512 L=8", kind, kw, x, msg, 2)
+
+
 @pytest.mark.parametrize("ebn0", [1, 2, 3] if FULL else [2])
 def test_c4_ca_fast_scl_lut_n1024(q, ebn0):
-    """C4: CAFastSCLLUTDecoder N=1024, A=512 + CRC-24 (K=536), L=8.  Tables: the N=1024 MinDistortion set (the MMI
-    generator of the reference needs its C++ quantizer package, which cannot be built here -- SURVEY 8c)."""
+    """the same class on the LLR-domain (MinDistortion) tables of the north-star benchmark"""
     N, A, K = 1024, 512, 536
     z, f, g = _n1024_tables()
     fm, mm = sim.frozen_mask(N, K)
@@ -150,18 +198,26 @@ def test_c4_ca_fast_scl_lut_n1024(q, ebn0):
     _check(q, "C4 CAFastSCL-LUT N=1024 A=512 K=536 L=8", "CAFastSCLLUTDecoder", kw, x, msg, ebn0)
 
 
-def test_c5_scl_uniform_n2048_l32(q):
-    """C5: SCLUniformQuantizedDecoder N=2048, A=K=1024, L=32, v=16; inputs pre-quantized by the driver's uniform
-    quantizer (mainQuantizedDecoder_ContinuousDomain.py:29-32); polarization-weight frozen set (the NR table stops at
-    1024)."""
+def c5_case(frames, ebn0=2.0, seed=500):
+    """C5 the way the continuous-domain driver sets it up (mainQuantizedDecoder_ContinuousDomain.py:95-104,186-192): frozen set
+    from PolarCodeConstructor.GA(sigma) -- the NR table stops at N=1024 --, step sizes from
+    LLRLSUniformQuantizer.generate_uniform_quantizers(sigma), channel LLRs quantized by QUniform (:29-32) with the root
+    step decoder_r_f[0]."""
     N, K, v = 2048, 1024, 16
-    frames = 256 if FULL else 32
-    llr, msg = channel_frames(N, K, K, False, 2.0, frames, seed=500, construction="pw")
-    r = 1.0
+    sigma = sim.awgn_sigma(ebn0, K / N)
+    fm, mm = sim.frozen_mask_ga(N, K, sigma)
+    r_f, r_g = sim.uniform_quantizer_steps(N, v, sigma)
+    rng = np.random.default_rng(seed)
+    msg = rng.integers(0, 2, (frames, K), dtype=np.uint8)
+    llr = sim.awgn_llr(sim.polar_encode(msg, fm), sigma, rng)
+    r = r_f[0]
     M = (v // 2 - 0.5) * r
     x = np.where(np.abs(llr) > M, np.sign(llr) * (M - 0.5 * r), (np.floor(llr / r) + 0.5) * r)
-    fm, mm = sim.frozen_mask(N, K, "pw")
-    rng = np.random.default_rng(5)
-    kw = dict(N=N, K=K, L=32, frozen_bits=fm, message_bits=mm, decoder_r_f=rng.uniform(0.5, 1.0, N - 1),
-              decoder_r_g=rng.uniform(0.5, 1.0, N - 1), v=v)
-    _check(q, "C5 SCL-Uniform N=2048 A=1024 L=32 v=16", "SCLUniformQuantizedDecoder", kw, x, msg, 2.0)
+    kw = dict(N=N, K=K, L=32, frozen_bits=fm, message_bits=mm, decoder_r_f=r_f, decoder_r_g=r_g, v=v)
+    return kw, x, msg
+
+
+def test_c5_scl_uniform_n2048_l32(q):
+    """C5: SCLUniformQuantizedDecoder N=2048, A=K=1024, L=32, v=16 with the reference's own construction and step sizes."""
+    kw, x, msg = c5_case(256 if FULL else 32)
+    _check(q, "C5 SCL-Uniform N=2048 A=1024 L=32 v=16 (GA construction, optimal uniform steps)", "SCLUniformQuantizedDecoder", kw, x, msg, 2.0)

@@ -112,7 +112,7 @@ def test_oracle_matches_reference_on_real_mindistortion_luts(tag, kind):
 def test_oracle_matches_compiled_reference_on_benchmark_workload(refmod):
     """The benchmark's real N=1024 MinDistortion tables: many duplicated / zero LLR quanta, i.e. constant ties."""
     import bench
-    kw, sym, msg = bench.make_workload(12, seed=4)
+    kw, sym, msg = bench.make_workload(bench.CONFIGS["NS"], 12, seed=4)
     want = common.ref_decode(refmod, "SCLLUTDecoder", kw, sym.astype(np.int32))
     got = po.OracleDecoder("SCLLUTDecoder", **kw).decode(sym.astype(np.int32))
     assert (got == want).all()

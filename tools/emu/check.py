@@ -44,6 +44,9 @@ CASES = [
     ("cafast", "CAFastSCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, B=8)),
     ("cafast_q", "CAFastSCLLUTDecoder", dict(N=256, K=152, A=128, L=4, B=24, Q=12, Qc=9)),
     ("multi_pass", "SCLLUTDecoder", dict(N=128, K=64, L=8, B=1001)),
+    ("staged_io", "SCLLUTDecoder", dict(N=128, K=64, L=4, B=9000)),
+    ("multidev", "SCLLUTDecoder", dict(N=128, K=64, L=4, B=9000)),
+    ("multidev_f64", "SCLDecoder", dict(N=128, K=64, L=4, B=3000, tables="channel")),
     ("multi_pass_l1", "SCLUTDecoder", dict(N=64, K=30, B=3000)),
     ("sclut_1024", "SCLUTDecoder", dict(N=1024, K=512, B=200, tables="minsum")),
     ("cascl_1024", "CASCLLUTDecoder", dict(N=1024, K=536, A=512, L=8, B=16, tables="minsum")),
@@ -64,6 +67,8 @@ def main():
         kw, x, _ = common.make_case(kind, seed=77, **ckw)
         t0 = time.time()
         dec = getattr(emu, kind)(**kw)
+        if name.startswith("multidev"):
+            dec.set_devices([0, 0, 0])
         got = dec.decode(x)
         t1 = time.time()
         want = po.OracleDecoder(kind, **kw).decode(x)

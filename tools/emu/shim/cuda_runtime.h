@@ -50,7 +50,7 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
-enum { cudaHostAllocMapped = 2, cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+enum { cudaHostAllocMapped = 2, cudaHostAllocDefault = 0, cudaHostAllocPortable = 1, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 2; char name[64] = "emulated sm_100"; };
@@ -82,6 +82,10 @@ static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (void *)1; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type = cudaMemoryTypeUnregistered; };
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaFuncSetAttribute(const void *, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, const void *, int threads, size_t smem) {
@@ -232,5 +236,6 @@ template <class T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; ret
 template <class T> static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
 template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
+static inline void __nanosleep(unsigned) {}
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
