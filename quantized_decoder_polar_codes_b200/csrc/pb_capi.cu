@@ -41,6 +41,10 @@ const void *scl_fn_l3_plain(bool ca);
 const void *scl_fn_l3_fast(bool ca);
 const void *scl_fn_l01(int logL, bool ca, bool fast);
 const void *scl_fn_l2(bool ca, bool fast);
+const void *scl_fn_l3_plain_priv(bool ca);
+const void *scl_fn_l3_fast_priv(bool ca);
+const void *scl_fn_l01_priv(int logL, bool ca, bool fast);
+const void *scl_fn_l2_priv(bool ca, bool fast);
 const void *path_fn_lut(int logL);
 const void *path_fn_float(int logL);
 const void *path_fn_uniform(int logL);
@@ -52,7 +56,12 @@ cudaError_t launch_optls(int n_problems, size_t smem, const double *density, con
 cudaError_t launch_mmi_table(int P, int M, int W, int mode, const double *p1, const double *p2, const double *l1, const double *l2,
                              double c1, double c2, double *out1, double *out2);
 cudaError_t launch_mmi_dp(int P, int M, int K, int W, const double *T, int32_t *lm, int32_t *Az);
-const void *fast_kernel_fn(int logL, bool ca, bool fast) {
+const void *fast_kernel_fn(int logL, bool ca, bool fast, bool priv) {
+    if (priv) {
+        if (logL >= 3) return fast ? scl_fn_l3_fast_priv(ca) : scl_fn_l3_plain_priv(ca);
+        if (logL == 2) return scl_fn_l2_priv(ca, fast);
+        return scl_fn_l01_priv(logL, ca, fast);
+    }
     if (logL >= 3) return fast ? scl_fn_l3_fast(ca) : scl_fn_l3_plain(ca);
     if (logL == 2) return scl_fn_l2(ca, fast);
     return scl_fn_l01(logL, ca, fast);
@@ -962,8 +971,12 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
             if (sl.ws_cap < wsn) { cudaFree(sl.ws); sl.ws = nullptr; sl.ws_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.ws, wsn)); sl.ws_cap = wsn; }
         }
     }
+    static const bool trace = getenv("POLAR_B200_TRACE") != nullptr;
+#define PD_TRACE(...) do { if (trace) { fprintf(stderr, "[pd_decode] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
+    PD_TRACE("B=%lld chunk=%lld units=%d narrow=%d stage_in=%d stage_out=%d", (long long)B, (long long)chunk, U, (int)narrow, (int)stage_in, (int)stage_out);
     HostPool &pool = HostPool::get();
     const int parts = pool.size();
+    PD_TRACE("pool of %d threads", parts);
     std::atomic<int> bad_value{0};
     const int n_slots = 2 * U;
     std::vector<int64_t> pend_f0(n_slots, -1), pend_nb(n_slots, 0);
@@ -973,7 +986,9 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
         pd_decoder *u = units[w % U];
         StreamSlot &sl = u->slot[w / U];
         CUDA_TRY(cudaSetDevice(u->device));
+        PD_TRACE("drain slot %d: wait", w);
         CUDA_TRY(cudaEventSynchronize(sl.done));     // the chunk's copies are done: both pinned areas of the slot are free again
+        PD_TRACE("drain slot %d: done", w);
         if (stage_out) {
             const size_t bytes = (size_t)pend_nb[w] * Ko, per = (bytes / parts + 63) & ~(size_t)63;
             uint8_t *dst = host_out + (size_t)pend_f0[w] * Ko;
@@ -1007,14 +1022,17 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
             });
             h2d_src = sl.h_in;
         }
+        PD_TRACE("chunk at %lld (%lld frames) staged -> slot %d", (long long)f0, (long long)nb, which);
         CUDA_TRY(cudaMemcpyAsync(sl.d_in, h2d_src, (size_t)nb * N * dsz, cudaMemcpyHostToDevice, sl.stream));
         if ((rc = launch(u, sl.d_in, dev_dtype, nb, sl.d_out, sl.stream, sl.ws))) return rc;
+        PD_TRACE("chunk at %lld launched", (long long)f0);
         CUDA_TRY(cudaMemcpyAsync(stage_out ? (void *)sl.h_out : (void *)(host_out + (size_t)f0 * Ko), sl.d_out, (size_t)nb * Ko, cudaMemcpyDeviceToHost, sl.stream));
         CUDA_TRY(cudaEventRecord(sl.done, sl.stream));
         pend_f0[which] = f0; pend_nb[which] = nb;
     }
     for (int k = 0; k < n_slots; ++k, which = (which + 1) % n_slots)
         if ((rc = drain(which))) return rc;
+    PD_TRACE("all chunks drained");
     rc = PD_OK;
     for (pd_decoder *u : units) {
         CUDA_TRY(cudaSetDevice(u->device));

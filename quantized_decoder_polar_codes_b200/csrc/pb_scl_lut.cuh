@@ -33,6 +33,9 @@
 #include "pb_generic.cuh"
 #include "pb_internal.h"
 
+#ifndef PB_DEFAULT_RING_PRIVATE
+#define PB_DEFAULT_RING_PRIVATE false     // which table ring plan_fast_lut picks when POLAR_B200_RING is not set
+#endif
 #ifndef PB_EXP_LINE
 #define PB_EXP_LINE 0
 #endif
@@ -65,6 +68,8 @@ struct FastParams {
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
     int warps;                     // consumer warps per CTA; one more warp streams the tables
+    int flags;                     // experiment knobs (POLAR_B200_KFLAGS): 1 = fork counts on the fp64 pipe, 2 = relaxed stage hand-back
+    int priv;                      // the kernel is a PRIV instantiation (private per-warp rings, no producer warp)
     int no_tma;                    // debug knob (POLAR_B200_NO_TMA): the producer warp copies the stages with plain loads / stores
     int warp_words;                // shared-memory words of one consumer warp (its V, X, scratch, fork cells)
     int vwords, xwords, scrwords;  // shared-memory words per lane: value levels gl+1..top, X; scratch words per warp
@@ -117,6 +122,7 @@ __device__ __forceinline__ uint4 lds128(smaddr_t a) {
 __device__ __forceinline__ void mbar_init(smaddr_t b, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(count)); }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(smaddr_t b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_relaxed(smaddr_t b) { asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory"); }
 __device__ __forceinline__ void mbar_wait(smaddr_t b, unsigned parity) {   // returns once the phase of that parity is complete
     // (the third operand is a suspend-time hint: the waiting warp sleeps in hardware instead of spinning on issue slots)
     asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
@@ -128,6 +134,35 @@ __device__ __forceinline__ void bulk_load(smaddr_t dst, const void *gsrc, unsign
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
 }
 #endif
+
+// Private ring (PRIV kernels): every lane copies ITS 16 bytes of a chunk with cp.async into a ring owned by its warp -- no
+// barrier, no producer warp; kPrivChunks - 1 chunks in flight per lane.
+constexpr int kPrivChunks = 4;
+#ifdef PB_HOST_EMU
+__device__ __forceinline__ void cp_async16(smaddr_t dst, const void *gsrc) { memcpy(reinterpret_cast<void *>(dst), gsrc, 16); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() {}
+#else
+__device__ __forceinline__ void cp_async16(smaddr_t dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.commit_group;\n" ::"r"(dst), "l"(gsrc) : "memory");
+}
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory"); }
+#endif
+// `fetch` = byte offset (inside the lane's column of the stream) of the next chunk to request; wraps at the end of the stream
+__device__ __forceinline__ uint4 priv_next_chunk(uint32_t &cc, uint32_t &fetch, smaddr_t ring_lane, const char *stream_lane, uint32_t stream_bytes) {
+    const uint32_t slot = cc & (kPrivChunks - 1);
+    cp_async16(ring_lane + ((slot + kPrivChunks - 1) & (kPrivChunks - 1)) * 512u, stream_lane + fetch);   // refill the slot consumed before
+    fetch += 512u;
+    if (fetch == stream_bytes) fetch = 0u;
+    cp_async_wait<kPrivChunks - 1>();                                                                     // ... and make sure this chunk has landed
+    ++cc;
+    return lds128(ring_lane + slot * 512u);
+}
+static __device__ __noinline__ uint4 priv_fetch_outlined(uint32_t cc, uint32_t fetch, smaddr_t ring_lane, const char *stream_lane) {
+    const uint32_t slot = cc & (kPrivChunks - 1);
+    cp_async16(ring_lane + ((slot + kPrivChunks - 1) & (kPrivChunks - 1)) * 512u, stream_lane + fetch);
+    cp_async_wait<kPrivChunks - 1>();
+    return lds128(ring_lane + slot * 512u);
+}
 
 // R1 nodes of the list Fast decoders: elements packed as rank<<5 | index, one column of a [element][32 lanes] array of
 // 16-bit words; std::sort order under "rank < rank" (equal ranks = equal |llr|: libstdc++'s introsort order)
@@ -145,32 +180,36 @@ static __device__ __noinline__ void sort_r1_packed(unsigned short *col, int n) {
 // Consumer side of the stream ring.  `cc` counts the chunks this warp has consumed since the kernel started; the ring slot,
 // the stage and the barrier phase follow from it.  The first chunk of a stage waits for the stage's "full" barrier, the last
 // one hands the stage back ("empty", one arrival per consumer warp).
-__device__ __forceinline__ uint4 ring_next_chunk(uint32_t &cc, smaddr_t ring_lane, smaddr_t bars, int lane) {
+// `last_refilled` = first chunk of the stages that the producer never refills (the last kStages of the launch): nobody waits
+// for their hand-back, and an arrive still in flight when the CTA retires could land on the barrier of the NEXT CTA that
+// gets this shared memory (it initialises its barriers right away) -- so those are not sent.
+__device__ __forceinline__ uint4 ring_next_chunk(uint32_t &cc, smaddr_t ring_lane, smaddr_t bars, int lane, uint32_t last_refilled, int relaxed = 0) {
     const uint32_t slot = cc & (kRingSlots - 1), st = slot / kCPS;
     if ((cc & (kCPS - 1)) == 0) mbar_wait(bars + st * 8u, (cc / kRingSlots) & 1u);
     const uint4 v = lds128(ring_lane + slot * 512u);
-    if ((cc & (kCPS - 1)) == kCPS - 1) {
+    if ((cc & (kCPS - 1)) == kCPS - 1 && cc < last_refilled) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(bars + (kStages + st) * 8u);
+        if (lane == 0) {
+#ifndef PB_HOST_EMU
+            if (relaxed) mbar_arrive_relaxed(bars + (kStages + st) * 8u);
+            else
+#endif
+            mbar_arrive(bars + (kStages + st) * 8u);
+        }
     }
     ++cc;
     return v;
 }
 // out-of-line variant for the Fast-SSC kernels (~40 consumption sites)
-static __device__ __noinline__ uint4 ring_fetch_outlined(uint32_t cc, smaddr_t ring_lane, smaddr_t bars, int lane) {
-    return ring_next_chunk(cc, ring_lane, bars, lane);
+static __device__ __noinline__ uint4 ring_fetch_outlined(uint32_t cc, smaddr_t ring_lane, smaddr_t bars, int lane, uint32_t last_refilled) {
+    return ring_next_chunk(cc, ring_lane, bars, lane, last_refilled);
 }
 struct LineState {
     uint32_t cc;   // chunks consumed so far
+    uint32_t fetch;   // PRIV: stream offset of the next chunk to request
     uint4 cur;     // the chunk lines are currently taken from
     int q;         // next line inside `cur` (4 = exhausted)
 };
-__device__ __forceinline__ uint32_t next_line_inl(LineState &ls, smaddr_t ring_lane, smaddr_t bars, int lane) {
-    if (ls.q == 4) { ls.cur = ring_next_chunk(ls.cc, ring_lane, bars, lane); ls.q = 0; }
-    const uint32_t v = ls.q == 0 ? ls.cur.x : ls.q == 1 ? ls.cur.y : ls.q == 2 ? ls.cur.z : ls.cur.w;
-    ++ls.q;
-    return v;
-}
 
 // 4 symbol bytes -> 4 nibbles (16 bits)
 __device__ __forceinline__ uint32_t pack4(uint32_t x) {
@@ -180,7 +219,7 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x) {
 // One CTA = fp.warps consumer warps, each decoding its own frame groups, + one producer warp that streams the tables
 // (6 CTAs of 4+1 warps per SM at N=1024, L=8 = 24 decoding warps: 64 registers per thread at most; the Fast variants, which
 // live with fewer resident warps, may take 96).
-template <int LOGL, bool CA, bool FAST>
+template <int LOGL, bool CA, bool FAST, bool PRIV>
 __global__ void __launch_bounds__((kMaxWarps + 1) * 32, FAST ? 4 : 6)
 scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastParams fp, const void *__restrict__ in, int in_dtype,
                     uint8_t *__restrict__ out, long long B, uint32_t *__restrict__ ws, int *err_flag, double *dbg_pm, int *dbg_win) {
@@ -198,14 +237,18 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     //      a line.  The host lays the lines out in consumption order, 4 lines per lane-transposed 512-byte chunk; the
     //      producer warp moves them stage by stage into the CTA's ring with TMA bulk copies, the consumer warps read their
     //      16 bytes per chunk with one LDS.128.  full[s] / empty[s] mbarriers carry the hand-over. ----
-    uint32_t *RINGB = sm + (size_t)W * fp.warp_words;
+    //      PRIV kernels: no producer warp and no barriers; each warp keeps a private ring that its lanes fill with
+    //      cp.async (priv_next_chunk).
+    uint32_t *RINGB = sm + (size_t)W * fp.warp_words + (PRIV ? (size_t)wid * (kPrivChunks * 128) : (size_t)0);
     const smaddr_t ring0 = (smaddr_t)__cvta_generic_to_shared(RINGB);
     const smaddr_t bars = ring0 + kRingSlots * 512u;          // full[kStages], empty[kStages]
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(bars + i * 8u, 1u); mbar_init(bars + (kStages + i) * 8u, (unsigned)W); }
-        mbar_fence_init();
+    if (!PRIV) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < kStages; ++i) { mbar_init(bars + i * 8u, 1u); mbar_init(bars + (kStages + i) * 8u, (unsigned)W); }
+            mbar_fence_init();
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // static schedule: in pass p, warp w of CTA b decodes frame group (p * gridDim.x + b) * W + w; a CTA runs as many
     // passes as its warp 0 has groups (warps without a group still drain the stream)
     const long long n_groups = (B + FPW - 1) / FPW;
@@ -213,7 +256,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     const long long first = (long long)blockIdx.x * W;
     const int n_pass = first < n_groups ? (int)((n_groups - first + per_pass - 1) / per_pass) : 0;
     const uint32_t spp = (uint32_t)fp.n_chunks / kCPS;        // stages per pass (the stream is padded to whole stages)
-    if (wid == W) {                                           // ---- producer warp
+    if (!PRIV && wid == W) {                                  // ---- producer warp
         if (fp.no_tma) {
             const uint4 *src = reinterpret_cast<const uint4 *>(fp.stream);
             uint4 *ring4 = reinterpret_cast<uint4 *>(RINGB);
@@ -260,15 +303,31 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     uint32_t *G = ws + ((size_t)blockIdx.x * W + wid) * fp.gwords * 32;  // value levels 1..gl, [word][lane], L2-resident
 
     LineState ls;
-    ls.cc = 0u; ls.cur = make_uint4(0, 0, 0, 0); ls.q = 4;
+    ls.cc = 0u; ls.fetch = 0u; ls.cur = make_uint4(0, 0, 0, 0); ls.q = 4;
+    const uint32_t total_stages = (uint32_t)n_pass * spp;
+    const uint32_t last_refilled = (total_stages > (uint32_t)kStages ? total_stages - kStages : 0u) * kCPS;   // chunks of stages that get refilled
     const smaddr_t ring_lane = ring0 + (unsigned)lane * 16u;   // this lane's 16 bytes of slot 0
+    const char *stream_lane = reinterpret_cast<const char *>(fp.stream) + lane * 16;
+    const uint32_t stream_bytes = (uint32_t)fp.n_chunks * 512u;
+    if (PRIV && n_pass > 0)
+        for (int i = 0; i < kPrivChunks - 1; ++i) { cp_async16(ring_lane + i * 512u, stream_lane + ls.fetch); ls.fetch += 512u; if (ls.fetch == stream_bytes) ls.fetch = 0u; }
     // the Fast-SSC variant has ~40 consumption sites: there the stream accessors are real (out-of-line) functions so
     // that the hot code stays inside the instruction cache; the plain variant inlines them
     auto next_chunk = [&]() -> uint4 {
+        if (PRIV) {
+            if (FAST && L > 1) {
+                const uint4 v = priv_fetch_outlined(ls.cc, ls.fetch, ring_lane, stream_lane);
+                ++ls.cc;
+                ls.fetch += 512u;
+                if (ls.fetch == stream_bytes) ls.fetch = 0u;
+                return v;
+            }
+            return priv_next_chunk(ls.cc, ls.fetch, ring_lane, stream_lane, stream_bytes);
+        }
 #ifdef PB_RING_VERIFY
         if (fp.no_tma == 2) {   // debug build only: check every chunk read from the ring against the stream in global memory
             const uint32_t c0 = ls.cc;
-            uint4 v = ring_next_chunk(ls.cc, ring_lane, bars, lane);
+            uint4 v = ring_next_chunk(ls.cc, ring_lane, bars, lane, last_refilled);
             const uint32_t nch = (uint32_t)fp.n_chunks, k = c0 % nch;
             const uint4 *gs = reinterpret_cast<const uint4 *>(fp.stream);
             const uint4 e = __ldg(gs + (size_t)k * 32 + lane);
@@ -285,11 +344,11 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         }
 #endif
         if (FAST && L > 1) {
-            const uint4 v = ring_fetch_outlined(ls.cc, ring_lane, bars, lane);
+            const uint4 v = ring_fetch_outlined(ls.cc, ring_lane, bars, lane, last_refilled);
             ++ls.cc;
             return v;
         }
-        return ring_next_chunk(ls.cc, ring_lane, bars, lane);
+        return ring_next_chunk(ls.cc, ring_lane, bars, lane, last_refilled, fp.flags & 2);
     };
     // upper-level steps and special nodes take their lines one at a time out of the current chunk.  In the Fast-SSC
     // variant `cur` is a queue with the next line in .x (no selects at the many call sites)
@@ -301,7 +360,10 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             ++ls.q;
             return v;
         }
-        return next_line_inl(ls, ring_lane, bars, lane);
+        if (ls.q == 4) { ls.cur = next_chunk(); ls.q = 0; }
+        const uint32_t v = ls.q == 0 ? ls.cur.x : ls.q == 1 ? ls.cur.y : ls.q == 2 ? ls.cur.z : ls.cur.w;
+        ++ls.q;
+        return v;
     };
     // eight f (or g) lookups for one word of symbols: out nibble k = T[u_k][a_k][b_k] with a_k / b_k nibble k of A / Bv.
     // Even and odd nibbles are split into byte lanes so that shuffle sources (a*2 + b>>3) and nibble shifts ((b&7)*4)
@@ -340,12 +402,13 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
 
     for (int pass = 0; pass < n_pass; ++pass) {
         const long long g = ((long long)pass * gridDim.x + blockIdx.x) * W + wid;
+        if (PRIV && g >= n_groups) break;
         if (g >= n_groups) {   // no group left for this warp: hand the pass's stages straight back
             for (uint32_t s2 = 0; s2 < spp; ++s2, ls.cc += kCPS) {
                 const uint32_t st = (ls.cc & (kRingSlots - 1)) / kCPS;
                 mbar_wait(bars + st * 8u, (ls.cc / kRingSlots) & 1u);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bars + (kStages + st) * 8u);
+                if (lane == 0 && ls.cc < last_refilled) mbar_arrive(bars + (kStages + st) * 8u);
             }
             continue;
         }
@@ -506,6 +569,38 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             *reinterpret_cast<double2 *>(&KS[(me * FPW + grp) * 2]) = make_double2(K0, K1);
             __syncwarp();
             int r0 = 0, r1 = 0;
+#ifndef PB_HOST_EMU
+            if (fp.flags & 1) {
+                // experiment: count on the fp64 pipe (predicated DADD) instead of the integer ALU, which is the busiest pipe
+                double c0 = 0., c1 = 0., c2 = 0., c3 = 0.;
+#pragma unroll
+                for (int j = 0; j < L; ++j) {
+                    const double2 kf = *reinterpret_cast<const double2 *>(&KS[(j * FPW + grp) * 2]);
+                    asm("{\n"
+                        " .reg .pred lt0, le0, f0, le1, lt1, lf1, jb, t0, t1;\n"
+                        " setp.lt.s32 jb, %8, %9;\n"
+                        " setp.lt.f64 lt0, %4, %6;\n"
+                        " setp.le.f64 le0, %4, %6;\n"
+                        " setp.lt.f64 f0, %5, %6;\n"
+                        " setp.le.f64 le1, %4, %7;\n"
+                        " setp.lt.f64 lt1, %5, %7;\n"
+                        " setp.le.f64 lf1, %5, %7;\n"
+                        " and.pred t0, jb, le0;\n"
+                        " or.pred t0, t0, lt0;\n"
+                        " and.pred t1, jb, lf1;\n"
+                        " or.pred t1, t1, lt1;\n"
+                        " @t0 add.f64 %0, %0, 0d3FF0000000000000;\n"
+                        " @f0 add.f64 %1, %1, 0d3FF0000000000000;\n"
+                        " @le1 add.f64 %2, %2, 0d3FF0000000000000;\n"
+                        " @t1 add.f64 %3, %3, 0d3FF0000000000000;\n"
+                        "}\n"
+                        : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3)
+                        : "d"(kf.x), "d"(kf.y), "d"(K0), "d"(K1), "r"(j), "r"(me));
+                }
+                r0 = __double2int_rn(c0 + c1);
+                r1 = __double2int_rn(c2 + c3);
+            } else
+#endif
 #pragma unroll
             for (int j = 0; j < L; ++j) {
                 const double2 kf = *reinterpret_cast<const double2 *>(&KS[(j * FPW + grp) * 2]);
@@ -1008,8 +1103,10 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         }
         __syncwarp();
         // hand back a partly consumed last stage; the next pass starts on the next stage
-        if (ls.cc & (kCPS - 1)) {
-            if (lane == 0) mbar_arrive(bars + (kStages + (ls.cc & (kRingSlots - 1)) / kCPS) * 8u);
+        if (PRIV) {
+            while (ls.cc - cc_pass != spp * kCPS) (void)next_chunk();      // (the stream is padded to whole stages)
+        } else if (ls.cc & (kCPS - 1)) {
+            if (lane == 0 && ls.cc < last_refilled) mbar_arrive(bars + (kStages + (ls.cc & (kRingSlots - 1)) / kCPS) * 8u);
             ls.cc = (ls.cc + kCPS - 1) & ~(uint32_t)(kCPS - 1);
         }
 #ifdef PB_HOST_EMU
@@ -1018,6 +1115,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         (void)cc_pass;
 #endif
     }
+    if (PRIV) cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1040,12 +1138,12 @@ inline bool fast_upload(FastPlan *pl, const std::vector<T> &h, const T **out) {
 
 // Kernel instantiations live in their own translation units (pb_kernels.cu, compiled in parallel); the host side only
 // sees the dispatcher.
-const void *fast_kernel_fn(int logL, bool ca, bool fast);
+const void *fast_kernel_fn(int logL, bool ca, bool fast, bool priv);
 #ifdef PB_TU_SCL
-template <int LOGL, bool FAST>
+template <int LOGL, bool FAST, bool PRIV>
 inline const void *fast_kernel_fn_l(bool ca) {
-    if (LOGL == 0 || !ca) return PB_KFN(scl_lut_warp_kernel<LOGL, false, FAST>);
-    return PB_KFN(scl_lut_warp_kernel<LOGL, (LOGL > 0), FAST>);
+    if (LOGL == 0 || !ca) return PB_KFN(scl_lut_warp_kernel<LOGL, false, FAST, PRIV>);
+    return PB_KFN(scl_lut_warp_kernel<LOGL, (LOGL > 0), FAST, PRIV>);
 }
 #endif
 
@@ -1310,26 +1408,33 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     pl->logL = logL;
     pl->ca = d.ca != 0;
     pl->fastk = max_special >= 0;
-    const void *fn = fast_kernel_fn(logL, pl->ca, pl->fastk);
+    // Table ring: CTA-shared, filled by a producer warp with TMA bulk copies, or (POLAR_B200_RING=private) one private
+    // cp.async ring per warp
+    const char *ring_env = getenv("POLAR_B200_RING");
+    const bool priv = ring_env ? (ring_env[0] == 'p' || ring_env[0] == 'P') : PB_DEFAULT_RING_PRIVATE;
+    P.priv = priv ? 1 : 0;
+    const void *fn = fast_kernel_fn(logL, pl->ca, pl->fastk, priv);
     // CTA shape: as many consumer warps per CTA as keep the SM's warp slots full (the ring and the producer warp are
     // shared by the CTA); POLAR_B200_WARPS_PER_CTA overrides (tuning knob)
-    const size_t ring_bytes = (size_t)kRingSlots * 512 + 2 * kStages * 8;
+    const size_t ring_shared = (size_t)kRingSlots * 512 + 2 * kStages * 8, ring_priv = (size_t)kPrivChunks * 512;
+    auto smem_for = [&](int w) { return (size_t)w * P.warp_words * 4 + (priv ? (size_t)w * ring_priv : ring_shared); };
     int best_w = 0, best_occ = 0;
     const int want_w = getenv("POLAR_B200_WARPS_PER_CTA") ? atoi(getenv("POLAR_B200_WARPS_PER_CTA")) : 0;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); free_fast_plan(pl); return; }
     for (int w = kMaxWarps; w >= 1; --w) {
         if (want_w && w != std::min(want_w, kMaxWarps)) continue;
-        const size_t smem = (size_t)w * P.warp_words * 4 + ring_bytes;
+        const size_t smem = smem_for(w);
         if (smem > 200 * 1024) continue;
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (w + 1) * 32, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (w + (priv ? 0 : 1)) * 32, smem) != cudaSuccess) { cudaGetLastError(); continue; }
         if (occ * w > best_occ * best_w) { best_w = w; best_occ = occ; }
     }
     if (best_w < 1 || best_occ < 1) { free_fast_plan(pl); return; }
     P.warps = best_w;
+    P.flags = getenv("POLAR_B200_KFLAGS") ? atoi(getenv("POLAR_B200_KFLAGS")) : 0;
     P.no_tma = getenv("POLAR_B200_NO_TMA") ? atoi(getenv("POLAR_B200_NO_TMA")) : 0;
     if (const char *e = getenv("POLAR_B200_CTAS_PER_SM")) best_occ = std::max(1, std::min(best_occ, atoi(e)));   // tuning / debug knob
-    pl->smem = (size_t)best_w * P.warp_words * 4 + ring_bytes;
+    pl->smem = smem_for(best_w);
     pl->ws_bytes_per_cta = (size_t)P.gwords * 32 * 4 * best_w;
     pl->ctas_per_sm = best_occ;
     pl->name = "scl_lut_warp";
@@ -1348,7 +1453,7 @@ inline int launch_fast_lut(const Dev &d, const FastPlan &pl, const void *d_in, i
     const int grid = fast_grid(pl, B, sm_count);
     void *args[] = {(void *)&d, (void *)&pl.p, (void *)&d_in, (void *)&dtype, (void *)&d_out, (void *)&B, (void *)&ws,
                     (void *)&d_err, (void *)&dbg_pm, (void *)&dbg_win};
-    cudaError_t e = cudaLaunchKernel(fast_kernel_fn(pl.logL, pl.ca, pl.fastk), dim3(grid), dim3((pl.p.warps + 1) * 32), args, pl.smem, s);
+    cudaError_t e = cudaLaunchKernel(fast_kernel_fn(pl.logL, pl.ca, pl.fastk, pl.p.priv != 0), dim3(grid), dim3((pl.p.warps + (pl.p.priv ? 0 : 1)) * 32), args, pl.smem, s);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }
