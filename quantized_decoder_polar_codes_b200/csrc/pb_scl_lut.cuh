@@ -34,7 +34,7 @@
 #include "pb_internal.h"
 
 #ifndef PB_DEFAULT_RING_PRIVATE
-#define PB_DEFAULT_RING_PRIVATE false     // which table ring plan_fast_lut picks when POLAR_B200_RING is not set
+#define PB_DEFAULT_RING_PRIVATE true      // which table ring plan_fast_lut picks when POLAR_B200_RING is not set
 #endif
 #ifndef PB_EXP_LINE
 #define PB_EXP_LINE 0
@@ -68,7 +68,6 @@ struct FastParams {
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
     int warps;                     // consumer warps per CTA; one more warp streams the tables
-    int flags;                     // experiment knobs (POLAR_B200_KFLAGS): 1 = fork counts on the fp64 pipe, 2 = relaxed stage hand-back
     int priv;                      // the kernel is a PRIV instantiation (private per-warp rings, no producer warp)
     int no_tma;                    // debug knob (POLAR_B200_NO_TMA): the producer warp copies the stages with plain loads / stores
     int warp_words;                // shared-memory words of one consumer warp (its V, X, scratch, fork cells)
@@ -122,7 +121,6 @@ __device__ __forceinline__ uint4 lds128(smaddr_t a) {
 __device__ __forceinline__ void mbar_init(smaddr_t b, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(count)); }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(smaddr_t b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory"); }
-__device__ __forceinline__ void mbar_arrive_relaxed(smaddr_t b) { asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory"); }
 __device__ __forceinline__ void mbar_wait(smaddr_t b, unsigned parity) {   // returns once the phase of that parity is complete
     // (the third operand is a suspend-time hint: the waiting warp sleeps in hardware instead of spinning on issue slots)
     asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
@@ -132,6 +130,16 @@ __device__ __forceinline__ void mbar_wait(smaddr_t b, unsigned parity) {   // re
 __device__ __forceinline__ void bulk_load(smaddr_t dst, const void *gsrc, unsigned bytes, smaddr_t bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+// experiment (POLAR_B200_NO_TMA=3): the .shared::cta destination form, issued by the lane elect.sync picks
+__device__ __forceinline__ void bulk_load_cta(smaddr_t dst, const void *gsrc, unsigned bytes, smaddr_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    unsigned p;
+    asm volatile("{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n selp.u32 %0, 1, 0, q;\n}\n" : "=r"(p));
+    return p != 0;
 }
 #endif
 
@@ -180,29 +188,20 @@ static __device__ __noinline__ void sort_r1_packed(unsigned short *col, int n) {
 // Consumer side of the stream ring.  `cc` counts the chunks this warp has consumed since the kernel started; the ring slot,
 // the stage and the barrier phase follow from it.  The first chunk of a stage waits for the stage's "full" barrier, the last
 // one hands the stage back ("empty", one arrival per consumer warp).
-// `last_refilled` = first chunk of the stages that the producer never refills (the last kStages of the launch): nobody waits
-// for their hand-back, and an arrive still in flight when the CTA retires could land on the barrier of the NEXT CTA that
-// gets this shared memory (it initialises its barriers right away) -- so those are not sent.
-__device__ __forceinline__ uint4 ring_next_chunk(uint32_t &cc, smaddr_t ring_lane, smaddr_t bars, int lane, uint32_t last_refilled, int relaxed = 0) {
+__device__ __forceinline__ uint4 ring_next_chunk(uint32_t &cc, smaddr_t ring_lane, smaddr_t bars, int lane) {
     const uint32_t slot = cc & (kRingSlots - 1), st = slot / kCPS;
     if ((cc & (kCPS - 1)) == 0) mbar_wait(bars + st * 8u, (cc / kRingSlots) & 1u);
     const uint4 v = lds128(ring_lane + slot * 512u);
-    if ((cc & (kCPS - 1)) == kCPS - 1 && cc < last_refilled) {
+    if ((cc & (kCPS - 1)) == kCPS - 1) {
         __syncwarp();
-        if (lane == 0) {
-#ifndef PB_HOST_EMU
-            if (relaxed) mbar_arrive_relaxed(bars + (kStages + st) * 8u);
-            else
-#endif
-            mbar_arrive(bars + (kStages + st) * 8u);
-        }
+        if (lane == 0) mbar_arrive(bars + (kStages + st) * 8u);
     }
     ++cc;
     return v;
 }
 // out-of-line variant for the Fast-SSC kernels (~40 consumption sites)
-static __device__ __noinline__ uint4 ring_fetch_outlined(uint32_t cc, smaddr_t ring_lane, smaddr_t bars, int lane, uint32_t last_refilled) {
-    return ring_next_chunk(cc, ring_lane, bars, lane, last_refilled);
+static __device__ __noinline__ uint4 ring_fetch_outlined(uint32_t cc, smaddr_t ring_lane, smaddr_t bars, int lane) {
+    return ring_next_chunk(cc, ring_lane, bars, lane);
 }
 struct LineState {
     uint32_t cc;   // chunks consumed so far
@@ -272,6 +271,22 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 }
             return;
         }
+#ifndef PB_HOST_EMU
+        if (fp.no_tma == 3) {
+            const char *src = reinterpret_cast<const char *>(fp.stream);
+            uint32_t i = 0;
+            for (int p = 0; p < n_pass; ++p)
+                for (uint32_t s = 0; s < spp; ++s, ++i) {
+                    const uint32_t st = i & (kStages - 1);
+                    if (elect_one()) {
+                        mbar_wait(bars + (kStages + st) * 8u, ((i / kStages) & 1u) ^ 1u);
+                        bulk_load_cta(ring0 + st * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bars + st * 8u);
+                    }
+                    __syncwarp();
+                }
+            return;
+        }
+#endif
         // TMA producer.  The WHOLE warp stays in the loop and lane 0 issues: with lanes 1..31 retired and lane 0 left alone
         // to wait and issue, the L = 1 kernels stopped (or faulted) as soon as an SM held its full complement of CTAs --
         // measured on B200, round 2 (profiles/r2/README.md); the copy loop of a full warp (POLAR_B200_NO_TMA=1) and this
@@ -304,8 +319,6 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
 
     LineState ls;
     ls.cc = 0u; ls.fetch = 0u; ls.cur = make_uint4(0, 0, 0, 0); ls.q = 4;
-    const uint32_t total_stages = (uint32_t)n_pass * spp;
-    const uint32_t last_refilled = (total_stages > (uint32_t)kStages ? total_stages - kStages : 0u) * kCPS;   // chunks of stages that get refilled
     const smaddr_t ring_lane = ring0 + (unsigned)lane * 16u;   // this lane's 16 bytes of slot 0
     const char *stream_lane = reinterpret_cast<const char *>(fp.stream) + lane * 16;
     const uint32_t stream_bytes = (uint32_t)fp.n_chunks * 512u;
@@ -327,7 +340,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
 #ifdef PB_RING_VERIFY
         if (fp.no_tma == 2) {   // debug build only: check every chunk read from the ring against the stream in global memory
             const uint32_t c0 = ls.cc;
-            uint4 v = ring_next_chunk(ls.cc, ring_lane, bars, lane, last_refilled);
+            uint4 v = ring_next_chunk(ls.cc, ring_lane, bars, lane);
             const uint32_t nch = (uint32_t)fp.n_chunks, k = c0 % nch;
             const uint4 *gs = reinterpret_cast<const uint4 *>(fp.stream);
             const uint4 e = __ldg(gs + (size_t)k * 32 + lane);
@@ -344,11 +357,11 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         }
 #endif
         if (FAST && L > 1) {
-            const uint4 v = ring_fetch_outlined(ls.cc, ring_lane, bars, lane, last_refilled);
+            const uint4 v = ring_fetch_outlined(ls.cc, ring_lane, bars, lane);
             ++ls.cc;
             return v;
         }
-        return ring_next_chunk(ls.cc, ring_lane, bars, lane, last_refilled, fp.flags & 2);
+        return ring_next_chunk(ls.cc, ring_lane, bars, lane);
     };
     // upper-level steps and special nodes take their lines one at a time out of the current chunk.  In the Fast-SSC
     // variant `cur` is a queue with the next line in .x (no selects at the many call sites)
@@ -408,7 +421,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 const uint32_t st = (ls.cc & (kRingSlots - 1)) / kCPS;
                 mbar_wait(bars + st * 8u, (ls.cc / kRingSlots) & 1u);
                 __syncwarp();
-                if (lane == 0 && ls.cc < last_refilled) mbar_arrive(bars + (kStages + st) * 8u);
+                if (lane == 0) mbar_arrive(bars + (kStages + st) * 8u);
             }
             continue;
         }
@@ -569,38 +582,6 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             *reinterpret_cast<double2 *>(&KS[(me * FPW + grp) * 2]) = make_double2(K0, K1);
             __syncwarp();
             int r0 = 0, r1 = 0;
-#ifndef PB_HOST_EMU
-            if (fp.flags & 1) {
-                // experiment: count on the fp64 pipe (predicated DADD) instead of the integer ALU, which is the busiest pipe
-                double c0 = 0., c1 = 0., c2 = 0., c3 = 0.;
-#pragma unroll
-                for (int j = 0; j < L; ++j) {
-                    const double2 kf = *reinterpret_cast<const double2 *>(&KS[(j * FPW + grp) * 2]);
-                    asm("{\n"
-                        " .reg .pred lt0, le0, f0, le1, lt1, lf1, jb, t0, t1;\n"
-                        " setp.lt.s32 jb, %8, %9;\n"
-                        " setp.lt.f64 lt0, %4, %6;\n"
-                        " setp.le.f64 le0, %4, %6;\n"
-                        " setp.lt.f64 f0, %5, %6;\n"
-                        " setp.le.f64 le1, %4, %7;\n"
-                        " setp.lt.f64 lt1, %5, %7;\n"
-                        " setp.le.f64 lf1, %5, %7;\n"
-                        " and.pred t0, jb, le0;\n"
-                        " or.pred t0, t0, lt0;\n"
-                        " and.pred t1, jb, lf1;\n"
-                        " or.pred t1, t1, lt1;\n"
-                        " @t0 add.f64 %0, %0, 0d3FF0000000000000;\n"
-                        " @f0 add.f64 %1, %1, 0d3FF0000000000000;\n"
-                        " @le1 add.f64 %2, %2, 0d3FF0000000000000;\n"
-                        " @t1 add.f64 %3, %3, 0d3FF0000000000000;\n"
-                        "}\n"
-                        : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3)
-                        : "d"(kf.x), "d"(kf.y), "d"(K0), "d"(K1), "r"(j), "r"(me));
-                }
-                r0 = __double2int_rn(c0 + c1);
-                r1 = __double2int_rn(c2 + c3);
-            } else
-#endif
 #pragma unroll
             for (int j = 0; j < L; ++j) {
                 const double2 kf = *reinterpret_cast<const double2 *>(&KS[(j * FPW + grp) * 2]);
@@ -1106,7 +1087,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         if (PRIV) {
             while (ls.cc - cc_pass != spp * kCPS) (void)next_chunk();      // (the stream is padded to whole stages)
         } else if (ls.cc & (kCPS - 1)) {
-            if (lane == 0 && ls.cc < last_refilled) mbar_arrive(bars + (kStages + (ls.cc & (kRingSlots - 1)) / kCPS) * 8u);
+            if (lane == 0) mbar_arrive(bars + (kStages + (ls.cc & (kRingSlots - 1)) / kCPS) * 8u);
             ls.cc = (ls.cc + kCPS - 1) & ~(uint32_t)(kCPS - 1);
         }
 #ifdef PB_HOST_EMU
@@ -1431,7 +1412,6 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     }
     if (best_w < 1 || best_occ < 1) { free_fast_plan(pl); return; }
     P.warps = best_w;
-    P.flags = getenv("POLAR_B200_KFLAGS") ? atoi(getenv("POLAR_B200_KFLAGS")) : 0;
     P.no_tma = getenv("POLAR_B200_NO_TMA") ? atoi(getenv("POLAR_B200_NO_TMA")) : 0;
     if (const char *e = getenv("POLAR_B200_CTAS_PER_SM")) best_occ = std::max(1, std::min(best_occ, atoi(e)));   // tuning / debug knob
     pl->smem = smem_for(best_w);

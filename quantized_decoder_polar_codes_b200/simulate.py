@@ -23,9 +23,6 @@ class Simulator:
         self.N = self.lib.pd_code_len(decoder._handle)
         self.kout = self.lib.pd_out_len(decoder._handle)
         self.A = int(A)
-        if self.kout != self.A:
-            raise ValueError(f"the decoder returns {self.kout} bits per frame but the messages have A={self.A}: with a CRC use a "
-                             "CRC-aided class (it returns the A message bits); pd_count_errors compares [B][A] rows")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         fb = np.ascontiguousarray(frozen_bits, dtype=np.int32)
         K = int((fb == 0).sum())
@@ -64,6 +61,9 @@ class Simulator:
     def run(self, ebn0_db, frames, batch=1 << 16, seed=0, max_block_errors=None, rank=0, world=1):
         """Decodes `frames` frames (this rank's contiguous share of them) at one Eb/N0 point.  `max_block_errors`
         reproduces the drivers' early stop (> 1000 block errors, :184), checked between batches."""
+        if self.kout != self.A:
+            raise ValueError(f"the decoder returns {self.kout} bits per frame but the messages have A={self.A}: with a CRC use a "
+                             "CRC-aided class (it returns the A message bits); pd_count_errors compares [B][A] rows")
         sigma = awgn_sigma(ebn0_db, self.rate)
         lo, hi = D.shard_range(frames, rank, world)
         s = torch.cuda.current_stream(self.device).cuda_stream
