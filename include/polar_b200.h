@@ -47,7 +47,9 @@ typedef enum pd_kind {
 typedef enum pd_dtype {
     PD_U8 = 0,   /* channel symbols, one byte each (LUT family; the compact streaming format)       */
     PD_I32 = 1,  /* channel symbols as the reference's py::array_t<int> (LUT family)                */
-    PD_F64 = 2   /* channel LLRs as the reference's py::array_t<double> (float/uniform/Lloyd family) */
+    PD_F64 = 2   /* channel LLRs as the reference's py::array_t<double> (float/uniform/Lloyd family); pd_decode (host buffers)
+                    also takes float64-TYPED SYMBOLS for the LUT family -- the probability-domain driver keeps them so,
+                    mainQuantizedDecoder_ProbabilityDomain.py:174-179 -- and truncates them to bytes like the reference's cast */
 } pd_dtype;
 
 typedef enum pd_status {
@@ -230,6 +232,10 @@ int pd_mmi_design(const double *p1, const double *p2, const double *l1, const do
 int64_t pd_launch_count(void);
 /* Name of the kernel variant pd_decode* uses for this decoder ("generic", "scl_lut_warp", ...). */
 const char *pd_kernel_name(const pd_decoder *dec);
+/* Why a LUT-class decoder is NOT on "scl_lut_warp" ("" when it is, or for the float / uniform / Lloyd classes): the shape
+   rule that sent it to the slower path_warp / generic kernels.  The same text is printed once on stderr at pd_create
+   (POLAR_B200_QUIET=1 silences it). */
+const char *pd_kernel_note(const pd_decoder *dec);
 /* Static description of the schedule for reports: n_steps, algorithmic lookups per frame, ... */
 int pd_schedule_stats(const pd_decoder *dec, int64_t *n_steps, int64_t *elem_ops, int64_t *n_sorts);
 

@@ -23,6 +23,8 @@ def lib():
         L.pd_version.restype = C.c_char_p
         L.pd_kernel_name.restype = C.c_char_p
         L.pd_kernel_name.argtypes = [C.c_void_p]
+        L.pd_kernel_note.restype = C.c_char_p
+        L.pd_kernel_note.argtypes = [C.c_void_p]
         L.pd_launch_count.restype = C.c_int64
         L.pd_out_len.argtypes = [C.c_void_p]
         L.pd_code_len.argtypes = [C.c_void_p]

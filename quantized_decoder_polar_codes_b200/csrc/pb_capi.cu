@@ -220,6 +220,39 @@ bool narrow_i32_to_u8(const int32_t *src, uint8_t *dst, size_t n) {
     return (bad & 0xffffff00u) == 0;
 }
 
+// n float64 symbols -> bytes (the probability-domain drivers keep their symbols in float64 arrays; the reference's pybind
+// layer casts them to int by truncation); false if a value does not fit a byte
+bool narrow_f64_to_u8(const double *src, uint8_t *dst, size_t n) {
+    uint32_t bad = 0;
+    size_t i = 0;
+#if defined(__SSE2__)
+    const bool nt = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    __m128i acc = _mm_setzero_si128();
+    for (; i + 16 <= n; i += 16) {
+        __m128i q[4];
+        for (int k = 0; k < 4; ++k) {
+            const __m128i lo = _mm_cvttpd_epi32(_mm_loadu_pd(src + i + 4 * k)), hi = _mm_cvttpd_epi32(_mm_loadu_pd(src + i + 4 * k + 2));
+            q[k] = _mm_unpacklo_epi64(lo, hi);
+        }
+        acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(q[0], q[1]), _mm_or_si128(q[2], q[3])));
+        const __m128i r = _mm_packus_epi16(_mm_packs_epi32(q[0], q[1]), _mm_packs_epi32(q[2], q[3]));
+        if (nt) _mm_stream_si128((__m128i *)(dst + i), r);
+        else _mm_storeu_si128((__m128i *)(dst + i), r);
+    }
+    if (nt) _mm_sfence();
+    alignas(16) uint32_t lanes[4];
+    _mm_store_si128((__m128i *)lanes, acc);
+    bad = lanes[0] | lanes[1] | lanes[2] | lanes[3];
+#endif
+    for (; i < n; ++i) {
+        const double v = src[i];
+        const int32_t t = (v > -1.0 && v < 256.0) ? (int32_t)v : -1;
+        bad |= (uint32_t)t;
+        dst[i] = (uint8_t)t;
+    }
+    return (bad & 0xffffff00u) == 0;
+}
+
 bool is_pinned(const void *p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -486,7 +519,13 @@ int plan_generic(pd_decoder *D) {
 
 size_t ws_need(const pd_decoder *D, int dtype, const void *d_in, int64_t B);
 bool want_fast(const pd_decoder *D, int dtype, const void *d_in) {
-    return D->fast.ok && dtype != PD_F64 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && D->force == 0;
+    if (D->fast.ok && dtype != PD_F64 && D->force == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) {
+        static std::atomic<bool> told{false};
+        if (!told.exchange(true) && !getenv("POLAR_B200_QUIET"))
+            fprintf(stderr, "[polar_b200] note: input pointer %p is not 16-byte aligned: this call runs on the slower 'path_warp' / 'generic' kernel\n", d_in);
+        return false;
+    }
+    return D->fast.ok && dtype != PD_F64 && D->force == 0;
 }
 bool want_path(const pd_decoder *D, int dtype, const void *d_in) {
     return !want_fast(D, dtype, d_in) && D->path.ok && D->force != 1;
@@ -511,7 +550,7 @@ int launch(pd_decoder *D, const void *d_in, int dtype, int64_t B, uint8_t *d_out
 
 // bytes of global workspace the kernel chosen for this call needs
 size_t ws_need(const pd_decoder *D, int dtype, const void *d_in, int64_t B) {
-    if (want_fast(D, dtype, d_in)) return D->fast.ws_bytes_per_cta * (size_t)fast_grid(D->fast, B, D->sm_count);
+    if (want_fast(D, dtype, d_in)) return pb::kWsHeadWords * 4 + D->fast.ws_bytes_per_cta * (size_t)fast_grid(D->fast, B, D->sm_count);
     if (want_path(D, dtype, d_in)) return D->path.ws_bytes_per_cta * (size_t)path_grid(D->path, B, D->sm_count);
     return D->use_smem ? 0 : D->ws_bytes * (size_t)generic_grid(D, B);
 }
@@ -525,9 +564,10 @@ int64_t wave_frames(const pd_decoder *D, int dtype, const void *d_in) {
 
 size_t dtype_size(int t) { return t == PD_U8 ? 1 : t == PD_I32 ? 4 : 8; }
 
-int check_dtype(const pd_decoder *D, int t) {
+int check_dtype(const pd_decoder *D, int t, bool host_call = false) {
     if (D->dev.domain == DOM_LUT) {
-        if (t != PD_U8 && t != PD_I32) return fail(PD_EINVAL, "LUT decoders take PD_U8 or PD_I32 symbols");
+        if (t == PD_F64 && host_call) return PD_OK;       // float64-typed symbols: narrowed to bytes on the host (pd_decode)
+        if (t != PD_U8 && t != PD_I32) return fail(PD_EINVAL, "LUT decoders take PD_U8 or PD_I32 symbols (pd_decode also PD_F64-typed symbols)");
     } else if (t != PD_F64) {
         return fail(PD_EINVAL, "float/uniform/Lloyd decoders take PD_F64 LLRs");
     }
@@ -689,6 +729,18 @@ int pd_create(const pd_config *c, pd_decoder **out) {
     plan_path_warp(D->dev, &D->path);
     if (const char *e = getenv("POLAR_B200_FORCE_GENERIC")) D->force = atoi(e);
     D->kernel_name = (D->fast.ok && D->force == 0) ? D->fast.name : (D->path.ok && D->force != 1) ? "path_warp" : "generic";
+    // a LUT class that falls off the nibble kernel runs 3-100x slower: say so once per reason (POLAR_B200_QUIET=1 silences it)
+    if (d.domain == DOM_LUT && !D->fast.ok && D->force == 0 && *D->fast.why && !getenv("POLAR_B200_QUIET")) {
+        static std::mutex mu;
+        static std::vector<std::string> seen;
+        std::lock_guard<std::mutex> lk(mu);
+        const std::string key = std::string(D->fast.why) + "/" + D->kernel_name;
+        if (std::find(seen.begin(), seen.end(), key) == seen.end()) {
+            seen.push_back(key);
+            fprintf(stderr, "[polar_b200] note: this LUT decoder (N=%d, L=%d) runs on the '%s' kernel, not 'scl_lut_warp': %s\n",
+                    N, d.list ? d.L : 1, D->kernel_name, D->fast.why);
+        }
+    }
     size_t in_frame = (size_t)N * (d.domain == DOM_LUT ? 4 : 8);
     D->chunk_frames = std::max<int64_t>(1024, (int64_t)((32u << 20) / in_frame));
     D->cfg.take(c);
@@ -750,6 +802,7 @@ int pd_out_len(const pd_decoder *D) { return D ? D->dev.Kout : 0; }
 int64_t pd_wave_frames(const pd_decoder *D, int in_dtype) { return D ? wave_frames(D, in_dtype, nullptr) : 0; }
 int pd_code_len(const pd_decoder *D) { return D ? D->dev.N : 0; }
 const char *pd_kernel_name(const pd_decoder *D) { return D ? D->kernel_name : ""; }
+const char *pd_kernel_note(const pd_decoder *D) { return (D && !D->fast.ok && D->dev.domain == DOM_LUT) ? D->fast.why : ""; }
 
 int pd_schedule_stats(const pd_decoder *D, int64_t *n_steps, int64_t *elem_ops, int64_t *n_sorts) {
     if (!D) return fail(PD_EINVAL, "null decoder");
@@ -919,11 +972,12 @@ int pd_decode_bd(pd_decoder *D, const double *llr, int64_t B, const int32_t *rnt
 
 int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8_t *host_out) {
     if (!D || (B > 0 && (!host_in || !host_out))) return fail(PD_EINVAL, "null argument");
-    int rc = check_dtype(D, in_dtype);
+    int rc = check_dtype(D, in_dtype, true);
     if (rc) return rc;
     if (B <= 0) return PD_OK;
     CUDA_TRY(cudaSetDevice(D->device));
     const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
+    const bool f64_symbols = in_dtype == PD_F64 && D->dev.domain == DOM_LUT;
     if (B * N * esz <= kSmallIn && B * Ko <= kSmallOut && !getenv("POLAR_B200_NO_MAPPED_IO")) {
         StreamSlot &sl = D->slot[0];
         if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
@@ -933,10 +987,15 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
             if (cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) { cudaFreeHost(hp); return fail(PD_ECUDA, "cudaHostGetDevicePointer failed"); }
             D->h_small = (char *)hp; D->d_small = (char *)dp;
         }
-        const size_t wsn = std::max(ws_need(D, in_dtype, D->d_small, B), (size_t)16);
+        const int small_dtype = f64_symbols ? PD_U8 : in_dtype;
+        const size_t wsn = std::max(ws_need(D, small_dtype, D->d_small, B), (size_t)16);
         if (sl.ws_cap < wsn) { cudaFree(sl.ws); sl.ws = nullptr; sl.ws_cap = 0; CUDA_TRY(cudaMalloc((void **)&sl.ws, wsn)); sl.ws_cap = wsn; }
-        memcpy(D->h_small, host_in, (size_t)B * N * esz);
-        if ((rc = launch(D, D->d_small, in_dtype, B, reinterpret_cast<uint8_t *>(D->d_small + kSmallIn), sl.stream, sl.ws))) return rc;
+        if (f64_symbols) {
+            if (!narrow_f64_to_u8((const double *)host_in, (uint8_t *)D->h_small, (size_t)B * N)) return fail(PD_ERANGE, "input symbol outside 0..255");
+        } else {
+            memcpy(D->h_small, host_in, (size_t)B * N * esz);
+        }
+        if ((rc = launch(D, D->d_small, small_dtype, B, reinterpret_cast<uint8_t *>(D->d_small + kSmallIn), sl.stream, sl.ws))) return rc;
         if ((rc = pd_check(D, sl.stream))) return rc;
         memcpy(host_out, D->h_small + kSmallIn, (size_t)B * Ko);
         return PD_OK;
@@ -946,7 +1005,7 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
     // stream slots per unit, so that the copies of one chunk hide behind the kernel of another.
     std::vector<pd_decoder *> units = D->units.empty() ? std::vector<pd_decoder *>{D} : D->units;
     const int U = (int)units.size();
-    const bool narrow = in_dtype == PD_I32 && D->fast.ok && D->force == 0;      // int32 symbols travel as bytes (4x less PCIe)
+    const bool narrow = (in_dtype == PD_I32 && D->fast.ok && D->force == 0) || f64_symbols;   // int32 / float64-typed symbols travel as bytes
     const size_t dsz = narrow ? 1 : esz;                                        // element size on the device
     const int dev_dtype = narrow ? PD_U8 : in_dtype;
     int64_t chunk = std::max<int64_t>(8192, (int64_t)((16u << 20) / (N * dsz)));
@@ -1017,7 +1076,8 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
                 const size_t o = (size_t)i * per;
                 if (o >= elems) return;
                 const size_t n = std::min(per, elems - o);
-                if (narrow) { if (!narrow_i32_to_u8((const int32_t *)src + o, (uint8_t *)dst + o, n)) bad_value = 1; }
+                if (f64_symbols) { if (!narrow_f64_to_u8((const double *)src + o, (uint8_t *)dst + o, n)) bad_value = 1; }
+                else if (narrow) { if (!narrow_i32_to_u8((const int32_t *)src + o, (uint8_t *)dst + o, n)) bad_value = 1; }
                 else memcpy(dst + o * esz, src + o * esz, n * esz);
             });
             h2d_src = sl.h_in;

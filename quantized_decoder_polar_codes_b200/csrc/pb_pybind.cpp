@@ -221,6 +221,8 @@ public:
             if (!in) throw py::value_error("decode: expected an array");
             if (py::isinstance<py::array_t<uint8_t>>(in) && (in.flags() & py::array::c_style)) {
                 arr = in; dtype = PD_U8;
+            } else if (py::isinstance<py::array_t<double>>(in) && (in.flags() & py::array::c_style)) {
+                arr = in; dtype = PD_F64;   // float64-typed symbols (probability-domain driver): pd_decode truncates them like the cast below
             } else {
                 arr = IArr::ensure(x);   // the reference takes py::array_t<int> with forcecast
                 dtype = PD_I32;
@@ -308,6 +310,7 @@ public:
     }
     int device_count() const { return pd_device_count(dec_); }
     std::string kernel() const { return pd_kernel_name(dec_); }
+    std::string kernel_note() const { return pd_kernel_note(dec_); }
     uintptr_t handle() const { return reinterpret_cast<uintptr_t>(dec_); }
 
 private:
@@ -327,6 +330,7 @@ py::class_<Cls<KIND>> declare(py::module_ &m, const char *name, const char *doc,
     py::class_<Cls<KIND>> c(m, name, doc);
     c.def("decode", &Decoder::decode, py::arg(decode_arg));
     c.def_property_readonly("kernel", &Decoder::kernel, "name of the CUDA kernel variant in use");
+    c.def_property_readonly("kernel_note", &Decoder::kernel_note, "why a LUT decoder is not on scl_lut_warp ('' when it is)");
     c.def("set_devices", &Decoder::set_devices, py::arg("device_ids"), "shard every decode() call over these CUDA devices of the box (pd_set_devices)");
     c.def_property_readonly("device_count", &Decoder::device_count);
     c.def_property_readonly("_handle", &Decoder::handle, "pd_decoder* for direct C-ABI calls");

@@ -50,6 +50,7 @@ constexpr int kRingSlots = kStages * kCPS;          // chunks in the ring
 constexpr unsigned kStageBytes = kCPS * 512u;
 constexpr int kMaxWarps = 4;                         // consumer warps per CTA (+ 1 producer warp)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWsHeadWords = 64;                     // launch state at the head of the workspace (256 bytes)
 
 enum FastOp : uint32_t {
     FOP_UF = 0, FOP_UG, FOP_UC,          // f / g / combine at depth <= top-1 (levels in memory)
@@ -68,6 +69,7 @@ struct FastParams {
     const uint32_t *crc_rem;       // [A] CRC remainder of each unit message bit (CA kinds)
     uint32_t crc_checkmask;
     int warps;                     // consumer warps per CTA; one more warp streams the tables
+    int dbg;                       // POLAR_B200_KDEBUG: 1 = never take the sorted-keeps shortcut in fork (A/B measurements)
     int priv;                      // the kernel is a PRIV instantiation (private per-warp rings, no producer warp)
     int no_tma;                    // debug knob (POLAR_B200_NO_TMA): the producer warp copies the stages with plain loads / stores
     int warp_words;                // shared-memory words of one consumer warp (its V, X, scratch, fork cells)
@@ -80,6 +82,7 @@ struct FastParams {
 
 struct FastPlan {
     bool ok = false;
+    const char *why = "";  // when !ok for a LUT class: which shape rule sent it to the slower kernels
     const char *name = "generic";
     int logL = 0;
     bool ca = false;
@@ -219,7 +222,7 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x) {
 // (6 CTAs of 4+1 warps per SM at N=1024, L=8 = 24 decoding warps: 64 registers per thread at most; the Fast variants, which
 // live with fewer resident warps, may take 96).
 template <int LOGL, bool CA, bool FAST, bool PRIV>
-__global__ void __launch_bounds__((kMaxWarps + 1) * 32, FAST ? 4 : 6)
+__global__ void __launch_bounds__((kMaxWarps + (PRIV ? 0 : 1)) * 32, PRIV ? (FAST ? 5 : 7) : (FAST ? 4 : 6))
 scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastParams fp, const void *__restrict__ in, int in_dtype,
                     uint8_t *__restrict__ out, long long B, uint32_t *__restrict__ ws, int *err_flag, double *dbg_pm, int *dbg_win) {
     constexpr int L = 1 << LOGL;
@@ -256,21 +259,6 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     const int n_pass = first < n_groups ? (int)((n_groups - first + per_pass - 1) / per_pass) : 0;
     const uint32_t spp = (uint32_t)fp.n_chunks / kCPS;        // stages per pass (the stream is padded to whole stages)
     if (!PRIV && wid == W) {                                  // ---- producer warp
-        if (fp.no_tma) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(fp.stream);
-            uint4 *ring4 = reinterpret_cast<uint4 *>(RINGB);
-            uint32_t i = 0;
-            for (int p = 0; p < n_pass; ++p)
-                for (uint32_t s = 0; s < spp; ++s, ++i) {
-                    const uint32_t st = i & (kStages - 1);
-                    mbar_wait(bars + (kStages + st) * 8u, ((i / kStages) & 1u) ^ 1u);
-                    for (int k = lane; k < (int)(kStageBytes / 16); k += 32) ring4[st * (kStageBytes / 16) + k] = __ldg(src + (size_t)s * (kStageBytes / 16) + k);
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bars + st * 8u);
-                }
-            return;
-        }
 #ifndef PB_HOST_EMU
         if (fp.no_tma == 3) {
             const char *src = reinterpret_cast<const char *>(fp.stream);
@@ -287,6 +275,21 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             return;
         }
 #endif
+        if (fp.no_tma) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(fp.stream);
+            uint4 *ring4 = reinterpret_cast<uint4 *>(RINGB);
+            uint32_t i = 0;
+            for (int p = 0; p < n_pass; ++p)
+                for (uint32_t s = 0; s < spp; ++s, ++i) {
+                    const uint32_t st = i & (kStages - 1);
+                    mbar_wait(bars + (kStages + st) * 8u, ((i / kStages) & 1u) ^ 1u);
+                    for (int k = lane; k < (int)(kStageBytes / 16); k += 32) ring4[st * (kStageBytes / 16) + k] = __ldg(src + (size_t)s * (kStageBytes / 16) + k);
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars + st * 8u);
+                }
+            return;
+        }
         // TMA producer.  The WHOLE warp stays in the loop and lane 0 issues: with lanes 1..31 retired and lane 0 left alone
         // to wait and issue, the L = 1 kernels stopped (or faulted) as soon as an SM held its full complement of CTAs --
         // measured on B200, round 2 (profiles/r2/README.md); the copy loop of a full warp (POLAR_B200_NO_TMA=1) and this
@@ -315,14 +318,15 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     double *R1S = reinterpret_cast<double *>(SEL + 32);                  // [7][32] smallest |llr| of an R1 node (Fast kinds)
     uint32_t *R1Q = reinterpret_cast<uint32_t *>(R1S + 7 * 32);          // [7][32] their positions
     unsigned short *R1P = reinterpret_cast<unsigned short *>(R1S);       // [32][32] packed sort keys of an R1 node (dead before R1S/R1Q are written)
-    uint32_t *G = ws + ((size_t)blockIdx.x * W + wid) * fp.gwords * 32;  // value levels 1..gl, [word][lane], L2-resident
+    // workspace: kWsHeadWords of launch state (word 0 = next frame group, PRIV kernels), then one region per resident warp
+    uint32_t *G = ws + kWsHeadWords + ((size_t)blockIdx.x * W + wid) * fp.gwords * 32;  // value levels 1..gl, [word][lane], L2-resident
 
     LineState ls;
     ls.cc = 0u; ls.fetch = 0u; ls.cur = make_uint4(0, 0, 0, 0); ls.q = 4;
     const smaddr_t ring_lane = ring0 + (unsigned)lane * 16u;   // this lane's 16 bytes of slot 0
     const char *stream_lane = reinterpret_cast<const char *>(fp.stream) + lane * 16;
     const uint32_t stream_bytes = (uint32_t)fp.n_chunks * 512u;
-    if (PRIV && n_pass > 0)
+    if (PRIV)
         for (int i = 0; i < kPrivChunks - 1; ++i) { cp_async16(ring_lane + i * 512u, stream_lane + ls.fetch); ls.fetch += 512u; if (ls.fetch == stream_bytes) ls.fetch = 0u; }
     // the Fast-SSC variant has ~40 consumption sites: there the stream accessors are real (out-of-line) functions so
     // that the hot code stays inside the instruction cache; the plain variant inlines them
@@ -413,9 +417,19 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
     };
     auto nib = [](uint32_t w, int k) -> uint32_t { return (w >> (4 * k)) & 15u; };
 
-    for (int pass = 0; pass < n_pass; ++pass) {
-        const long long g = ((long long)pass * gridDim.x + blockIdx.x) * W + wid;
-        if (PRIV && g >= n_groups) break;
+    for (int pass = 0; PRIV || pass < n_pass; ++pass) {
+        // PRIV kernels: the warps take their frame groups from a counter (zeroed by the host before the launch), so a warp
+        // that runs ahead -- they do, by a few per cent -- takes more of them and the launch ends without a tail.  The
+        // shared-ring kernels keep the static schedule (all warps of a CTA must consume the same number of passes).
+        long long g;
+        if (PRIV) {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(ws, 1u);
+            g = (long long)__shfl_sync(kFull, t, 0);
+            if (g >= n_groups) break;
+        } else {
+            g = ((long long)pass * gridDim.x + blockIdx.x) * W + wid;
+        }
         if (g >= n_groups) {   // no group left for this warp: hand the pass's stages straight back
             for (uint32_t s2 = 0; s2 < spp; ++s2, ls.cc += kCPS) {
                 const uint32_t st = (ls.cc & (kRingSlots - 1)) / kCPS;
@@ -461,6 +475,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         }
 
         double PM = (me == 0) ? 0.0 : d.pm_init;
+        bool srt = !(fp.dbg & 1) && d.pm_init >= 0.0;   // the path metrics are in non-decreasing slot order (see fork)
         // 3-bit-per-level slot pointers for levels 1..top: values (pv) and left-child partial sums (pu)
         uint32_t pv = 0x09249249u * (uint32_t)me, pu = pv;
         auto getp = [&](uint32_t pw, int lev) -> int { return (int)((pw >> (3 * (lev - 1))) & 7u); };
@@ -577,11 +592,44 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         // me, "keep") and K1 (index L+me, "flip"); the L smallest of the group's 2L keys in std::sort order survive.
         // For 2L <= 16 libstdc++ is an insertion sort, i.e. a stable rank of (key, index).  Returns the lane of the
         // parent path and the flip flag; PM, the pointer words and the subtree registers follow the parent.
-        auto fork = [&](double K0, double K1, int &p, uint32_t &fl) {
+        // `keeps_sorted`: the caller offers K0 = PM and no path metric has changed since the previous fork.  A fork leaves
+        // the metrics in rank order (slot r = r-th smallest key, equal keys in index order), so (keep_j, j) < (K0, me) is
+        // exactly j < me: that part of the rank is `me`, and a third of the compares goes away.  Uniform over the warp
+        // (it follows the frozen pattern, not the data).
+        auto fork = [&](double K0, double K1, int &p, uint32_t &fl, bool keeps_sorted) {
             __syncwarp();
             *reinterpret_cast<double2 *>(&KS[(me * FPW + grp) * 2]) = make_double2(K0, K1);
             __syncwarp();
             int r0 = 0, r1 = 0;
+            if (keeps_sorted) {
+                r0 = me;
+#pragma unroll
+                for (int j = 0; j < L; ++j) {
+                    const double2 kf = *reinterpret_cast<const double2 *>(&KS[(j * FPW + grp) * 2]);
+                    // r0 += flip_j < K0 ;  r1 += keep_j <= K1  +  (flip_j,j) < (K1,me)
+#ifdef PB_HOST_EMU
+                    if (j < me && !(kf.x <= K0)) { fprintf(stderr, "scl_lut_warp: fork called with keeps_sorted on unsorted metrics\n"); abort(); }
+                    r0 += (int)(kf.y < K0);
+                    r1 += (int)(kf.x <= K1) + (int)((kf.y < K1) || (kf.y <= K1 && j < me));
+#else
+                    asm("{\n"
+                        " .reg .pred f0, le1, lt1, lf1, jb, t1;\n"
+                        " setp.lt.s32 jb, %6, %7;\n"
+                        " setp.lt.f64 f0, %3, %4;\n"
+                        " setp.le.f64 le1, %2, %5;\n"
+                        " setp.lt.f64 lt1, %3, %5;\n"
+                        " setp.le.f64 lf1, %3, %5;\n"
+                        " and.pred t1, jb, lf1;\n"
+                        " or.pred t1, t1, lt1;\n"
+                        " @f0 add.s32 %0, %0, 1;\n"
+                        " @le1 add.s32 %1, %1, 1;\n"
+                        " @t1 add.s32 %1, %1, 1;\n"
+                        "}\n"
+                        : "+r"(r0), "+r"(r1)
+                        : "d"(kf.x), "d"(kf.y), "d"(K0), "d"(K1), "r"(j), "r"(me));
+#endif
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < L; ++j) {
                 const double2 kf = *reinterpret_cast<const double2 *>(&KS[(j * FPW + grp) * 2]);
@@ -613,6 +661,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                     : "d"(kf.x), "d"(kf.y), "d"(K0), "d"(K1), "r"(j), "r"(me));
 #endif
             }
+            }
             if (r0 < L) SEL[gbase + r0] = (uint32_t)me;
             if (r1 < L) SEL[gbase + r1] = (uint32_t)me | 16u;
             __syncwarp();
@@ -625,6 +674,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             xb = __shfl_sync(kFull, xb, p);
             pv = __shfl_sync(kFull, pv, p);
             pu = __shfl_sync(kFull, pu, p);
+            srt = !(fp.dbg & 1);
         };
         // LLR line: lane s holds the low word of entry s, lane 16+s its high word (sym < 16)
         auto llr_of = [&](uint32_t lr, uint32_t sym) -> double {
@@ -661,6 +711,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         // Fast-SSC special node (R0 / R1 / REP, plus SPC for the non-list decoder): the LLR of element j is
         // virtual_channel_llrs[dd-1][pos][symbol] (PD/src/FastSCLLUTDecoder.cpp:89,112,179), one stream line per element
         auto special = [&](int spt, int dd, uint32_t node) {
+            srt = false;      // special nodes add penalties to the path metrics
             const int temp = N >> dd;
             // the node's LLR lines start on a chunk boundary: four elements per chunk, no per-line bookkeeping
             // (the non-list R0 has no lines; the list R1 takes its rank lines one by one like the upper-level steps)
@@ -791,7 +842,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 }
                 int p;
                 uint32_t fl;
-                fork(a0, a1, p, fl);
+                fork(a0, a1, p, fl, false);
                 if (spt == 1) {      // the flipped position is the slot's OWN pre-permutation ordering
                     dec = __shfl_sync(kFull, dec, p);
                     if (fl) dec ^= 1u << q;
@@ -946,11 +997,12 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                             if (!frozen && DM <= 0) xb |= 1u << lp;
                         } else if (frozen) {
                             if (DM < 0) PM += fabs(DM);
+                            srt = false;
                         } else {
                             const uint32_t dec = (DM < 0) ? 1u : 0u;
                             int p;
                             uint32_t fl;
-                            fork(PM, PM + fabs(DM), p, fl);
+                            fork(PM, PM + fabs(DM), p, fl, srt);
                             xb |= (__shfl_sync(kFull, dec, p) ^ fl) << lp;
                         }
                     }
@@ -992,11 +1044,12 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                         bit = (!frozen && DM <= 0) ? 1u : 0u;
                     } else if (frozen) {
                         if (DM < 0) PM += fabs(DM);
+                        srt = false;
                     } else {
                         const uint32_t dec = (DM < 0) ? 1u : 0u;
                         int p;
                         uint32_t fl;
-                        fork(PM, PM + fabs(DM), p, fl);
+                        fork(PM, PM + fabs(DM), p, fl, srt);
                         bit = __shfl_sync(kFull, dec, p) ^ fl;
                     }
                     xb = (xb & ~(1u << lp)) | (bit << lp);
@@ -1136,17 +1189,18 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
                           const std::vector<double> &llr, const std::vector<uint32_t> &llr_off,
                           const int64_t *llr_off64, const int32_t *frozen, uint32_t crc_taps, FastPlan *pl) {
     pl->ok = false;
+    pl->why = "";
     if (!eligible_kind) return;
     const int N = d.N, n = d.n, L = d.list ? d.L : 1;
-    if (N < 32) return;
+    if (N < 32) { pl->why = "N < 32"; return; }
     int logL = 0;
     while ((1 << logL) < L) logL++;
-    if ((1 << logL) != L || L > 8) return;
-    if (d.list && L == 1) return;   // list rules with a single path (bit = llr<0, ...) differ from SC's: generic kernel
+    if ((1 << logL) != L || L > 8) { pl->why = "list size not in {1,2,4,8}"; return; }
+    if (d.list && L == 1) { pl->why = "list decoder with L = 1"; return; }   // list rules with a single path (bit = llr<0, ...) differ from SC's: generic kernel
     for (int p = 0; p < N - 1; ++p) {
         const NodeTab &t = tabs[p];
-        if (t.f_pstride || t.g_pstride) return;
-        if (t.f_qb > 16 || t.g_qb > 16 || t.f_sz / t.f_qb > 16 || t.g_sz / t.g_qb > 16) return;
+        if (t.f_pstride || t.g_pstride) { pl->why = "per-position tables inside a node"; return; }
+        if (t.f_qb > 16 || t.g_qb > 16 || t.f_sz / t.f_qb > 16 || t.g_sz / t.g_qb > 16) { pl->why = "a table wider than 16 x 16"; return; }
     }
     auto is_special = [&](int depth, int node) -> int {   // -1 or the special type
         if (max_special < 0 || depth >= n) return -1;
@@ -1191,7 +1245,7 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     auto push_llr_row = [&](int level, int pos) {
         int64_t r = (int64_t)level * N + pos;
         int len = (int)(llr_off64[r + 1] - llr_off64[r]);
-        if (len > 16) { ok = false; len = 16; }
+        if (len > 16) { ok = false; pl->why = "an LLR row longer than 16"; len = 16; }
         uint32_t line[32];
         memset(line, 0, sizeof line);
         for (int e = 0; e < len; ++e) {   // lane e: low word of entry e, lane 16+e: high word (llr_of)
@@ -1210,10 +1264,10 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         for (int j = 0; j < temp; ++j) {
             const int64_t r = (int64_t)(depth - 1) * N + node * temp + j;
             const int len = (int)(llr_off64[r + 1] - llr_off64[r]);
-            if (len > 16) { ok = false; return; }
+            if (len > 16) { ok = false; pl->why = "an LLR row longer than 16"; return; }
             for (int sidx = 0; sidx < len; ++sidx) {
                 const double v = llr[llr_off[r] + sidx];
-                if (v != v) { ok = false; return; }   // NaN has no rank: generic kernel
+                if (v != v) { ok = false; pl->why = "NaN in an LLR row of an R1 node"; return; }   // NaN has no rank: generic kernel
                 vals.push_back(std::fabs(v));
             }
         }
@@ -1244,7 +1298,7 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         const int p = heap(depth, node), temp = N >> depth;
         const int st = is_special(depth, node);
         if (st >= 0) {
-            if (L > 1 && st == 1) { has_r1 = true; if (temp > 32) ok = false; }
+            if (L > 1 && st == 1) { has_r1 = true; if (temp > 32) { ok = false; pl->why = "a list R1 node wider than 32 leaves"; } }
             emit(FOP_SP, depth, st, (uint32_t)node);
             if (L > 1 && st == 1) push_r1_ranks(depth, node);
             else if (!(L == 1 && st == 0))
@@ -1296,7 +1350,7 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         }
     };
     walk(0, 0);
-    if (!ok || ops.empty()) return;
+    if (!ok || ops.empty()) { if (!*pl->why) pl->why = "empty walk"; return; }
     op_lines.back().swap(stream);
     // assemble: every 16 ops one "op line" (op k of the batch = words 2k, 2k+1), then each op's own lines; a SUB8
     // op starts on a chunk boundary.  The ops thus ride the same prefetched stream as the tables they drive.
@@ -1361,7 +1415,7 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     int gl = 0, goff = std::max(1, (N / 8) * FPW / 32), soff = 0;
     // (the Fast-SSC walk is latency bound and gains 7 % from the extra resident warps of a 4-word cut; the plain walk is
     //  issue bound and indifferent: measured on N=1024, L=8)
-    const int smem_level_words = getenv("POLAR_B200_SMEM_LEVEL_WORDS") ? atoi(getenv("POLAR_B200_SMEM_LEVEL_WORDS")) : (max_special >= 0 ? 4 : 8);
+    const int smem_level_words = getenv("POLAR_B200_SMEM_LEVEL_WORDS") ? atoi(getenv("POLAR_B200_SMEM_LEVEL_WORDS")) : 4;
     P.voff[0] = 0;
     for (int lev = 1; lev <= n - 3; ++lev) {
         int words = (N >> lev) / 8;
@@ -1412,6 +1466,7 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     }
     if (best_w < 1 || best_occ < 1) { free_fast_plan(pl); return; }
     P.warps = best_w;
+    P.dbg = getenv("POLAR_B200_KDEBUG") ? atoi(getenv("POLAR_B200_KDEBUG")) : 0;
     P.no_tma = getenv("POLAR_B200_NO_TMA") ? atoi(getenv("POLAR_B200_NO_TMA")) : 0;
     if (const char *e = getenv("POLAR_B200_CTAS_PER_SM")) best_occ = std::max(1, std::min(best_occ, atoi(e)));   // tuning / debug knob
     pl->smem = smem_for(best_w);
@@ -1433,6 +1488,10 @@ inline int launch_fast_lut(const Dev &d, const FastPlan &pl, const void *d_in, i
     const int grid = fast_grid(pl, B, sm_count);
     void *args[] = {(void *)&d, (void *)&pl.p, (void *)&d_in, (void *)&dtype, (void *)&d_out, (void *)&B, (void *)&ws,
                     (void *)&d_err, (void *)&dbg_pm, (void *)&dbg_win};
+    if (pl.p.priv) {      // the group counter of the dynamic schedule
+        cudaError_t e0 = cudaMemsetAsync(ws, 0, kWsHeadWords * 4, s);
+        if (e0 != cudaSuccess) return (int)e0;
+    }
     cudaError_t e = cudaLaunchKernel(fast_kernel_fn(pl.logL, pl.ca, pl.fastk, pl.p.priv != 0), dim3(grid), dim3((pl.p.warps + (pl.p.priv ? 0 : 1)) * 32), args, pl.smem, s);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();

@@ -360,6 +360,16 @@ def test_host_call_staging_paths(q, monkeypatch, dtype):
     with pytest.raises(ValueError):
         dec.decode(bad)
     assert (dec.decode(x.astype(dtype)) == want).all()  # and the decoder stays usable
+    if dtype == "float64":                               # float64-typed symbols are truncated on the host like the reference's cast
+        assert (dec.decode(x[:3].astype(np.float64)) == want[:3]).all()       # tiny call: mapped staging area
+        assert (dec.decode(x.astype(np.float64) + 0.75) == want).all()
+        badf = x.astype(np.float64)
+        badf[5, 9] = np.nan
+        with pytest.raises(ValueError):
+            dec.decode(badf)
+        badf[5, 9] = -2.0
+        with pytest.raises(ValueError):
+            dec.decode(badf[4:8])
 
 
 def test_set_devices_shards_one_call(q, monkeypatch):

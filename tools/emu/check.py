@@ -45,6 +45,7 @@ CASES = [
     ("cafast_q", "CAFastSCLLUTDecoder", dict(N=256, K=152, A=128, L=4, B=24, Q=12, Qc=9)),
     ("multi_pass", "SCLLUTDecoder", dict(N=128, K=64, L=8, B=1001)),
     ("staged_io", "SCLLUTDecoder", dict(N=128, K=64, L=4, B=9000)),
+    ("staged_f64sym", "SCLLUTDecoder", dict(N=128, K=64, L=4, B=5000, xdtype="float64")),
     ("multidev", "SCLLUTDecoder", dict(N=128, K=64, L=4, B=9000)),
     ("multidev_f64", "SCLDecoder", dict(N=128, K=64, L=4, B=3000, tables="channel")),
     ("multi_pass_l1", "SCLUTDecoder", dict(N=64, K=30, B=3000)),
@@ -64,12 +65,14 @@ def main():
     for name, kind, ckw in CASES:
         if flt and flt not in name:
             continue
+        ckw = dict(ckw)
+        xdtype = ckw.pop("xdtype", None)
         kw, x, _ = common.make_case(kind, seed=77, **ckw)
         t0 = time.time()
         dec = getattr(emu, kind)(**kw)
         if name.startswith("multidev"):
             dec.set_devices([0, 0, 0])
-        got = dec.decode(x)
+        got = dec.decode(x if xdtype is None else x.astype(xdtype) + 0.5)   # (float64-typed symbols are truncated)
         t1 = time.time()
         want = po.OracleDecoder(kind, **kw).decode(x)
         bad = int((got != want).any(axis=1).sum())
