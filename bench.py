@@ -46,7 +46,7 @@ def _sim():
 
 # BASELINE.json configurations.  api_dtype = what the reference driver of that configuration hands to decode().
 CONFIGS = {
-    "NS": dict(kind="SCLLUTDecoder", N=1024, A=512, K=512, L=8, ebn0=2.0, dev_dtype="u8", api_dtype="int32", frames=131072,
+    "NS": dict(kind="SCLLUTDecoder", N=1024, A=512, K=512, L=8, ebn0=2.0, dev_dtype="u8", api_dtype="int32", frames=524288,
                workload="SCL-LUT N=1024 A=K=512 L=8 QDecoder=QChannel=16, MinDistortion LUTs (reference generator, design 3 dB), AWGN Eb/N0=2.0 dB through the driver's channel quantizer, NR-sequence frozen set",
                metric="decoded frames/s (info Gbit/s = frames/s*512/1e9), N=1024 L=8 SCL-LUT"),
     "C1": dict(kind="SCDecoder", N=128, A=64, K=64, L=1, ebn0=2.0, dev_dtype="f64", api_dtype="float64", frames=1 << 19,

@@ -826,20 +826,22 @@ int pd_decode_device(pd_decoder *D, const void *dev_in, int in_dtype, int64_t B,
     if (B <= 0) return PD_OK;
     CUDA_TRY(cudaSetDevice(D->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    // The decode kernels are persistent (every CTA walks several frame groups), so a single launch ends with a tail
-    // in which most SMs idle.  A large batch is therefore cut into kSplit pieces issued alternately on two internal
-    // streams forked from / joined to the caller's stream with events: the tail of one piece overlaps the next.
+    // One launch per call for the plain scl_lut_warp kernels with the private ring: their warps take frame groups from a
+    // counter, so the launch has no tail, and one value workspace (72 MB at N=1024, L=8) stays L2-resident.
+    // Every other persistent kernel (static schedule: path_warp, the shared-ring variants; and the Fast-SSC variants, which
+    // are instruction-fetch bound and run 30 % faster when the warps of an SM start their walks together) gets its batch in
+    // pieces of ONE wave, issued alternately on two internal streams forked from / joined to the caller's stream with
+    // events: the CTAs of piece k+1 move into the slots that the CTAs of piece k vacate, so nothing idles between pieces.
+    // POLAR_B200_FORCE_SPLIT=0/1 overrides, POLAR_B200_PIECE_WAVES sets the piece size.
     const size_t esz = dtype_size(in_dtype), N = D->dev.N, Ko = D->dev.Kout;
     const int64_t wave = wave_frames(D, in_dtype, dev_in);
-    constexpr int kSplit = 4;
-    // (Measured, round 2: also a batch of a whole number of waves gains 5 % from the split -- in one launch every warp of the
-    //  GPU walks the tree in the same phase, all forking or all streaming the big levels at once; overlapped launches are out
-    //  of phase and mix the pipes better.  POLAR_B200_FORCE_SPLIT=0/1 overrides.)
     static const int force_split = getenv("POLAR_B200_FORCE_SPLIT") ? atoi(getenv("POLAR_B200_FORCE_SPLIT")) : -1;
-    const bool split = force_split == 0 ? false : (wave > 0 && B >= (force_split == 1 ? 4 : 8) * wave && ((N * esz) % 16 == 0));
-    const int pieces = split ? kSplit : 1;
-    // pieces are whole waves of the persistent kernel (every warp of a piece runs the same number of passes)
-    const int64_t per = split ? ((((B + wave - 1) / wave) + kSplit - 1) / kSplit) * wave : B;
+    static const int piece_waves = getenv("POLAR_B200_PIECE_WAVES") ? std::max(1, atoi(getenv("POLAR_B200_PIECE_WAVES"))) : 1;
+    const bool dynamic_kernel = want_fast(D, in_dtype, dev_in) && D->fast.p.priv && !D->fast.fastk;
+    const bool split = force_split == 0 ? false
+                                        : ((force_split == 1 || !dynamic_kernel) && wave > 0 && B >= 2 * wave * piece_waves && ((N * esz) % 16 == 0));
+    const int64_t per = split ? wave * piece_waves : B;
+    const int pieces = split ? (int)((B + per - 1) / per) : 1;
     // workspace: one region per concurrently running piece
     const size_t need1 = ws_need(D, in_dtype, dev_in, per);
     const size_t need = need1 * (split ? 2 : 1);

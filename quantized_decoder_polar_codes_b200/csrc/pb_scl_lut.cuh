@@ -511,20 +511,25 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                 __syncwarp();
                 return;
             }
-            // One instance of the word loop per (source, destination) memory space -- workspace (global, L2) or shared --
-            // so that every access is a plain LDG/STG or LDS/STS with a running offset.  Operands of word w+1 are fetched
-            // while word w is looked up; the u bits of a g step come 32 at a time out of the partial-sum column.
             const int nw = ct >> 3;
             const uint32_t ub0 = (2u * node) * (uint32_t)ct;
             const int so = (dd == 0) ? grp : fp.voff[dd] * 32 + vslot(dd);
             const int dof = fp.voff[dd + 1] * 32 + lane;
             const int xo_ = (int)(ub0 >> 5) * 32 + uslot(dd + 1);
             const int ush = (int)(ub0 & 31u);
-            auto body = [&](auto sg_c, auto dg_c, auto isg_c) {
-                constexpr bool SG = decltype(sg_c)::value, DG = decltype(dg_c)::value, ISG = decltype(isg_c)::value;
-                const uint32_t *pa = (SG ? G : V) + so;
+            const bool sg = dd <= fp.gl, dg = dd + 1 <= fp.gl;   // (dd == 0: the packed channel words live in the workspace too)
+            // ONE word loop per step kind (f / g), source and destination space (workspace or shared memory) chosen at run
+            // time through generic pointers.  Round 2 had one instance per (source, destination) space -- plain LDG/LDS with
+            // running offsets, 1 % fewer instructions -- but six copies of the hottest loop: the kernel's code grew to 51 KB
+            // and, with the warps of an SM spread over the whole walk, instruction fetch became the limit (the same launch
+            // was 8 % faster as a sequence of fresh one-wave launches whose warps start in step).  Two copies: 41 KB, and the
+            // persistent launch runs 12 % faster (profiles/r2/README.md).  Operands of word w+1 are fetched while word w is
+            // looked up; the u bits of a g step come 32 at a time out of the partial-sum column.
+            auto body = [&](auto isg_c) {
+                constexpr bool ISG = decltype(isg_c)::value;
+                const uint32_t *pa = (sg ? G : V) + so;
+                uint32_t *pd = (dg ? G : V) + dof;
                 const uint32_t *pb = pa + nw * sstride;
-                uint32_t *pd = (DG ? G : V) + dof;
                 const uint32_t *px = X + xo_;
                 uint32_t A = *pa, Bv = *pb, xw = 0;
                 if (ISG) xw = *px >> ush;
@@ -541,18 +546,8 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                     }
                 }
             };
-            const bool sg = dd <= fp.gl, dg = dd + 1 <= fp.gl;   // (dd == 0: the packed channel words live in the workspace too)
-            using T_ = std::true_type;
-            using F_ = std::false_type;
-            if (isg) {
-                if (dg) body(T_{}, T_{}, T_{});
-                else if (sg) body(T_{}, F_{}, T_{});
-                else body(F_{}, F_{}, T_{});
-            } else {
-                if (dg) body(T_{}, T_{}, F_{});
-                else if (sg) body(T_{}, F_{}, F_{});
-                else body(F_{}, F_{}, F_{});
-            }
+            if (isg) body(std::true_type{});
+            else body(std::false_type{});
             if (L > 1) setown(pv, dd + 1);
             __syncwarp();
         };
@@ -601,7 +596,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
             *reinterpret_cast<double2 *>(&KS[(me * FPW + grp) * 2]) = make_double2(K0, K1);
             __syncwarp();
             int r0 = 0, r1 = 0;
-            if (keeps_sorted) {
+            if (!FAST && keeps_sorted) {     // (not in the Fast variants: code size, see fg_step)
                 r0 = me;
 #pragma unroll
                 for (int j = 0; j < L; ++j) {
@@ -975,7 +970,7 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
                         const uint32_t r1 = __funnelshift_r(((xb >> (pos - 1)) & 1u) ? b1 : b0, 0u, H2 >> 8);
                         w21 = w2p | ((r0 & 15u) << 16) | ((r1 & 15u) << 20);
                     }
-#pragma unroll
+#pragma unroll(FAST ? 1 : 2)
                     for (int side = 0; side < 2; ++side) {
                         // leaf symbol through the depth n-1 node: f table (left leaf) or g tables with u = left leaf's bit
                         const uint32_t cp = w21 >> 16;
@@ -1453,7 +1448,8 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
     // shared by the CTA); POLAR_B200_WARPS_PER_CTA overrides (tuning knob)
     const size_t ring_shared = (size_t)kRingSlots * 512 + 2 * kStages * 8, ring_priv = (size_t)kPrivChunks * 512;
     auto smem_for = [&](int w) { return (size_t)w * P.warp_words * 4 + (priv ? (size_t)w * ring_priv : ring_shared); };
-    int best_w = 0, best_occ = 0;
+    int best_w = 0, best_occ = 0, best_score = 0;
+    const int warp_cap = (pl->fastk && L > 1 && !getenv("POLAR_B200_CTAS_PER_SM")) ? 12 : 1 << 20;   // resident warps per SM wanted at most
     const int want_w = getenv("POLAR_B200_WARPS_PER_CTA") ? atoi(getenv("POLAR_B200_WARPS_PER_CTA")) : 0;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); free_fast_plan(pl); return; }
     for (int w = kMaxWarps; w >= 1; --w) {
@@ -1462,8 +1458,13 @@ inline void plan_fast_lut(const Dev &d, bool eligible_kind, const int32_t *node_
         if (smem > 200 * 1024) continue;
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (w + (priv ? 0 : 1)) * 32, smem) != cudaSuccess) { cudaGetLastError(); continue; }
-        if (occ * w > best_occ * best_w) { best_w = w; best_occ = occ; }
+        // The Fast-SSC list variants are bound by instruction fetch (65 KB of code, 39 % of the stall samples "no
+        // instruction"): every extra resident warp adds misses.  Measured on N=1024, L=8 (profiles/r2/README.md): 8 warps per
+        // SM 9.1e6 frames/s, 12: 8.9e6, 16: 8.6e6, 21 (all that fit): 7.7e6.  They get 12 warps, in CTAs of 4 when those fit.
+        const int score = std::min(occ * w, warp_cap);
+        if (score > best_score) { best_w = w; best_occ = occ; best_score = score; }
     }
+    if (best_w >= 1) best_occ = std::min(best_occ, std::max(1, warp_cap / best_w));
     if (best_w < 1 || best_occ < 1) { free_fast_plan(pl); return; }
     P.warps = best_w;
     P.dbg = getenv("POLAR_B200_KDEBUG") ? atoi(getenv("POLAR_B200_KDEBUG")) : 0;
