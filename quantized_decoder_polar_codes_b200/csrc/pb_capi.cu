@@ -1111,21 +1111,40 @@ int pd_decode(pd_decoder *D, const void *host_in, int in_dtype, int64_t B, uint8
 
 #ifndef PB_HOST_EMU
 // ---- simulation-mode error counters -------------------------------------------------------------
-__global__ void count_errors_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, long long B, int len,
+// `lpf` lanes per frame (a power of two, 32 / lpf frames per warp): the lanes read the two rows with 16-byte loads (rows of a
+// multiple of 16 bytes at 16-byte aligned bases: lpf = len / 16 rounded up to a power of two, at most 32; else byte by
+// byte, lane-strided, a warp per frame) -- HBM-bound, 2 * len bytes per frame.
+__device__ __forceinline__ unsigned nonzero_bytes(uint32_t x) {
+    return (unsigned)__popc((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);
+}
+__global__ void count_errors_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, long long B, int len, int lpf, int vec,
                                     unsigned long long *counters) {
+    const int lane = threadIdx.x & 31, li = lane & (lpf - 1), sub = lane / lpf, fpw = 32 / lpf;
+    const unsigned gmask = (lpf == 32 ? 0xffffffffu : ((1u << lpf) - 1u)) << (sub * lpf);
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     unsigned long long bits = 0, blocks = 0;
-    for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < B; f += (long long)gridDim.x * blockDim.x) {
-        const uint8_t *pa = a + (size_t)f * len, *pb = b + (size_t)f * len;
-        int e = 0;
-        for (int k = 0; k < len; ++k) e += (pa[k] != pb[k]);
+    for (long long base = warp * fpw; base < B; base += n_warps * fpw) {
+        const long long f = base + sub;
+        unsigned e = 0;
+        if (f < B) {
+            const uint8_t *pa = a + (size_t)f * len, *pb = b + (size_t)f * len;
+            if (vec) {
+                for (int k = li * 16; k < len; k += lpf * 16) {
+                    const uint4 x = __ldcs(reinterpret_cast<const uint4 *>(pa + k)), y = __ldcs(reinterpret_cast<const uint4 *>(pb + k));
+                    e += nonzero_bytes(x.x ^ y.x) + nonzero_bytes(x.y ^ y.y) + nonzero_bytes(x.z ^ y.z) + nonzero_bytes(x.w ^ y.w);
+                }
+            } else {
+                for (int k = li; k < len; k += lpf) e += (pa[k] != pb[k]);
+            }
+        }
         bits += e;
-        blocks += (e != 0);
+        if ((__ballot_sync(0xffffffffu, e != 0) & gmask) != 0u && li == 0) blocks++;
     }
     for (int o = 16; o > 0; o >>= 1) {
         bits += __shfl_down_sync(0xffffffffu, bits, o);
         blocks += __shfl_down_sync(0xffffffffu, blocks, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (bits) atomicAdd(&counters[0], bits);
         if (blocks) atomicAdd(&counters[1], blocks);
     }
@@ -1135,9 +1154,12 @@ int pd_count_errors(const uint8_t *dev_decoded, const uint8_t *dev_truth, int64_
                     unsigned long long *dev_counters, void *cuda_stream) {
     if (B <= 0) return PD_OK;
     if (!dev_decoded || !dev_truth || !dev_counters || len < 1) return fail(PD_EINVAL, "null argument");
-    int threads = 128;
-    int grid = (int)std::min<int64_t>((B + threads - 1) / threads, (int64_t)current_sm_count() * 8);
-    count_errors_kernel<<<grid, threads, 0, (cudaStream_t)cuda_stream>>>(dev_decoded, dev_truth, B, len, dev_counters);
+    const int vec = (len % 16 == 0) && (reinterpret_cast<uintptr_t>(dev_decoded) % 16 == 0) && (reinterpret_cast<uintptr_t>(dev_truth) % 16 == 0);
+    int lpf = 32;
+    if (vec) { lpf = 1; while (lpf < 32 && lpf * 16 < len) lpf *= 2; }
+    const int threads = 256, fpb = (threads / 32) * (32 / lpf);      // frames per block and iteration
+    const int grid = (int)std::min<int64_t>((B + fpb - 1) / fpb, (int64_t)current_sm_count() * 8);
+    count_errors_kernel<<<grid, threads, 0, (cudaStream_t)cuda_stream>>>(dev_decoded, dev_truth, B, len, lpf, vec, dev_counters);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return PD_OK;

@@ -278,6 +278,17 @@ def test_error_counters(q):
     capi.check(capi.lib().pd_count_errors(ta.data_ptr(), tb.data_ptr(), 1000, 37, cnt.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert cnt.cpu().tolist() == [int(flips.sum()), int(flips.any(axis=1).sum())]
+    # rows of a multiple of 16 bytes take the vector path (one warp per frame, 16 bytes per lane); any byte values count
+    for B, n in ((5000, 512), (333, 48), (70, 1024)):
+        a = rng.integers(0, 256, (B, n), dtype=np.uint8)
+        b = a.copy()
+        flips = rng.random(a.shape) < 0.003
+        b[flips] = (b[flips].astype(np.int32) + rng.integers(1, 256, int(flips.sum()))).astype(np.uint8)
+        ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        cnt.zero_()
+        capi.check(capi.lib().pd_count_errors(ta.data_ptr(), tb.data_ptr(), B, n, cnt.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert cnt.cpu().tolist() == [int(flips.sum()), int(flips.any(axis=1).sum())]
 
 
 def test_properties_at_full_size(q):
