@@ -1,5 +1,6 @@
 // scl_lut_warp: the specialised kernel for the LUT SC / SCL / CRC-aided SCL decoders
-// (SCLUTDecoder, SCLLUTDecoder, CASCLLUTDecoder -- SURVEY.md 8a rows a10, a14, a18; the north-star shape).
+// and their Fast-SSC variants (SCLUTDecoder, SCLLUTDecoder, CASCLLUTDecoder, FastSCLUTDecoder, FastSCLLUTDecoder,
+// CAFastSCLLUTDecoder -- SURVEY.md 8a rows a10, a12, a14, a16, a18, a19; a14 is the north-star shape).
 //
 // Mapping: one warp decodes 32/L codewords at once, ONE LANE PER LIST PATH (L in {1,2,4,8}); the tree walk is
 // the same for every frame, so the whole warp runs one uniform instruction stream and never diverges.
@@ -12,11 +13,16 @@
 //   * f / g lookups: the 16x16 nibble table of the node is ONE 32-bit register per lane (128 B per warp) and a
 //     lookup is a warp shuffle + shift (no bank conflicts, no shared memory);
 //   * every table / LLR row is consumed exactly once per pass and in a fixed order, so the host lays them out
-//     as one linear stream of 128-byte lines that each lane prefetches with cp.async into a private 16-slot
-//     ring in shared memory (L2 latency fully hidden, no register cost);
+//     as one linear stream of 128-byte lines.  Two ways to bring it on chip (template parameter PRIV):
+//     a private 4-chunk ring per warp that every lane fills with cp.async (default), or one ring per CTA that a
+//     producer warp fills with TMA bulk copies + mbarriers (POLAR_B200_RING=shared; see DESIGN.md 4.1 for why it
+//     is not the default);
 //   * fork: 2L path metrics ranked with a stable (key,index) count -- identical to libstdc++'s insertion sort
-//     for 2L <= 16 (PD/src/SCLLUTDecoder.cpp:8-22); keys are compared as the uint64 bit
-//     patterns of the non-negative fp64 metrics.
+//     for 2L <= 16 (PD/src/SCLLUTDecoder.cpp:8-22);
+//   * schedule: persistent CTAs of 4 warps; the PRIV kernels take frame groups from a counter in the workspace
+//     (dynamic), the shared-ring kernels walk a static schedule;
+//   * code size matters as much as instruction count: an SM's warps sit all over the walk, the instruction cache
+//     sees the whole kernel.
 // Output: the root partial sums x of the selected path are turned back into u = x F^{(x)n} and gathered.
 #pragma once
 #include <cuda_runtime.h>
@@ -48,7 +54,7 @@ constexpr int kStages = 4;
 constexpr int kCPS = 4;
 constexpr int kRingSlots = kStages * kCPS;          // chunks in the ring
 constexpr unsigned kStageBytes = kCPS * 512u;
-constexpr int kMaxWarps = 4;                         // consumer warps per CTA (+ 1 producer warp)
+constexpr int kMaxWarps = 4;                         // decoding warps per CTA (+ 1 producer warp in the shared-ring kernels)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWsHeadWords = 64;                     // launch state at the head of the workspace (256 bytes)
 
@@ -218,9 +224,9 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x) {
     return (x & 0xfu) | ((x >> 4) & 0xf0u) | ((x >> 8) & 0xf00u) | ((x >> 12) & 0xf000u);
 }
 
-// One CTA = fp.warps consumer warps, each decoding its own frame groups, + one producer warp that streams the tables
-// (6 CTAs of 4+1 warps per SM at N=1024, L=8 = 24 decoding warps: 64 registers per thread at most; the Fast variants, which
-// live with fewer resident warps, may take 96).
+// One CTA = fp.warps decoding warps, each working on its own frame groups (PRIV: 7 CTAs of 4 warps per SM at N=1024, L=8 =
+// 28 decoding warps, 72 registers per thread at most; the Fast variants, which run best with 12 resident warps, may take
+// 100), plus -- shared-ring kernels only -- one producer warp that streams the tables (6 CTAs of 4+1 warps, 64 registers).
 template <int LOGL, bool CA, bool FAST, bool PRIV>
 __global__ void __launch_bounds__((kMaxWarps + (PRIV ? 0 : 1)) * 32, PRIV ? (FAST ? 5 : 7) : (FAST ? 4 : 6))
 scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastParams fp, const void *__restrict__ in, int in_dtype,
