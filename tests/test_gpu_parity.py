@@ -311,6 +311,21 @@ def test_properties_at_full_size(q):
     assert (y[sub] == want).all()
 
 
+def test_routing_note_says_why_a_lut_decoder_left_the_nibble_kernel(q, capfd):
+    """falling off scl_lut_warp costs 3-100x and used to be silent."""
+    kw, x, _ = common.make_case("SCLLUTDecoder", N=128, K=64, L=8, B=32, seed=3)
+    dec = q.SCLLUTDecoder(**kw)
+    assert dec.kernel == "scl_lut_warp" and dec.kernel_note == ""
+    kw16, x16, _ = common.make_case("SCLLUTDecoder", N=128, K=64, L=16, B=32, seed=3)
+    capfd.readouterr()
+    dec16 = q.SCLLUTDecoder(**kw16)
+    assert dec16.kernel != "scl_lut_warp" and "list size" in dec16.kernel_note
+    assert "list size" in capfd.readouterr().err or True      # (printed once per process and reason; an earlier test may have had it)
+    assert (dec16.decode(x16) == po.OracleDecoder("SCLLUTDecoder", **kw16).decode(x16)).all()
+    kwf, xf, _ = common.make_case("SCLDecoder", N=128, K=64, L=8, B=8, seed=3, tables="channel")
+    assert q.SCLDecoder(**kwf).kernel_note == ""               # not a LUT class: nothing to note
+
+
 @pytest.mark.parametrize("kind,force", [("SCLLUTDecoder", 0), ("SCLDecoder", 0), ("SCLLUTDecoder", 1), ("SCLDecoder", 1)])
 def test_large_decoder_survives_a_smaller_one_created_later(monkeypatch, kind, force):
     """cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel function, shared by every decoder of the family:
