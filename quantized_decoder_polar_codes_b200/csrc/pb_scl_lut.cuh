@@ -298,8 +298,9 @@ scl_lut_warp_kernel(const __grid_constant__ Dev d, const __grid_constant__ FastP
         }
         // TMA producer.  The WHOLE warp stays in the loop and lane 0 issues: with lanes 1..31 retired and lane 0 left alone
         // to wait and issue, the L = 1 kernels stopped (or faulted) as soon as an SM held its full complement of CTAs --
-        // measured on B200, round 2 (profiles/r2/README.md); the copy loop of a full warp (POLAR_B200_NO_TMA=1) and this
-        // form both run every shape.
+        // measured on B200, round 2 (profiles/r2/README.md).  This form runs those shapes but still stops under CTA turnover
+        // (back-to-back one-wave launches on two streams); only the copy loop of a full warp (POLAR_B200_NO_TMA=1) runs
+        // everything.  Hence the private ring is the default.
         {
             const char *src = reinterpret_cast<const char *>(fp.stream);
             uint32_t i = 0;
