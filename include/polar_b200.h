@@ -109,8 +109,9 @@ void pd_destroy(pd_decoder *dec);
 int pd_out_len(const pd_decoder *dec);
 int pd_code_len(const pd_decoder *dec);
 /* Frames that one full wave of the (persistent) decode kernel holds in flight on the decoder's GPU: SMs x resident warps x
- * frames per warp; 0 for the CTA-per-frame generic kernel.  A batch that is a multiple of it keeps every warp busy until the
- * last frame (no tail); pd_decode_device cuts other large batches into overlapping launches instead. */
+ * frames per warp; 0 for the CTA-per-frame generic kernel.  The scl_lut_warp kernels hand frame groups to their warps from a
+ * counter, so any batch size runs without a tail in one launch; the statically scheduled kernels (fp64 family, Fast-SSC
+ * variants) get large batches as overlapping one-wave launches, and there a multiple of this number has no tail. */
 int64_t pd_wave_frames(const pd_decoder *dec, int in_dtype);
 
 /* Replaces `T::decode(array)` (e.g. SCLLUT::decode, PD/src/SCLLUTDecoder.cpp:47) for a batch of B frames.
